@@ -1,0 +1,142 @@
+"""Generate tests/golden/*.npz by running the reference's OWN python code (CPU, this container).
+
+    python tools/gen_golden.py
+
+The reference (/root/reference) does not travel to the GPU box; these small fixtures do.
+Covers SURVEY.md section 8(c): serialization codes for all four orders at several depths,
+Point.serialization order/inverse, get_padding_and_inverse, and the non-flash dense
+attention branch of SerializedAttention (fp32) -- forward output and input gradients.
+spconv is absent from the reference tree and from this image: no fixture can be generated
+for it (parity unpinned, see oracle/__init__.py).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tools import ref_import  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def gen_serialization():
+    ser = ref_import.load_serialization()
+    out = {}
+    rng = np.random.default_rng(1234)
+    cases = {"d3": (3, 300, 1), "d9": (9, 4000, 4), "d10": (10, 3000, 2), "d12": (12, 3000, 3), "d16": (16, 2000, 5)}
+    for name, (depth, n, nb) in cases.items():
+        gc = rng.integers(0, 1 << depth, size=(n, 3)).astype(np.int32)
+        gc[0] = 0
+        gc[1] = (1 << depth) - 1
+        b = np.sort(rng.integers(0, nb, size=n)).astype(np.int64)
+        out[f"{name}_grid"] = gc
+        out[f"{name}_batch"] = b
+        out[f"{name}_depth"] = np.int64(depth)
+        for order in ("z", "z-trans", "hilbert", "hilbert-trans"):
+            code = ser.encode(torch.from_numpy(gc), torch.from_numpy(b), depth, order=order)
+            out[f"{name}_{order}"] = code.numpy()
+    # survey appendix B points
+    P = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 2, 3), (7, 7, 7)], dtype=np.int32)
+    for depth in (3, 9, 16):
+        for order in ("z", "z-trans", "hilbert", "hilbert-trans"):
+            out[f"appB_d{depth}_{order}"] = ser.encode(torch.from_numpy(P), torch.zeros(6, dtype=torch.long), depth, order=order).numpy()
+    out["appB_points"] = P
+    np.savez_compressed(os.path.join(OUT, "serialization.npz"), **out)
+    print("serialization.npz", len(out), "arrays")
+
+
+def gen_point_and_padding():
+    ref = ref_import.load_models(use_shims=False)
+    Point = ref.structure.Point
+    SA = ref.ptv3.SerializedAttention
+    out = {}
+    # Point.serialization on unique voxels (ties are implementation-defined, so avoid them)
+    rng = np.random.default_rng(7)
+    n_per = [1500, 700, 2300]
+    gcs, bs = [], []
+    for bi, n in enumerate(n_per):
+        lin = rng.choice(64 * 64 * 64, size=n, replace=False)
+        gcs.append(np.stack([lin // 4096, (lin // 64) % 64, lin % 64], 1))
+        bs.append(np.full(n, bi))
+    gc = np.concatenate(gcs).astype(np.int32)
+    b = np.concatenate(bs).astype(np.int64)
+    p = Point(grid_coord=torch.from_numpy(gc), batch=torch.from_numpy(b), feat=torch.zeros(len(b), 1))
+    orders = ("z", "z-trans", "hilbert", "hilbert-trans")
+    p.serialization(order=orders, shuffle_orders=False)
+    out["ser_grid"] = gc
+    out["ser_batch"] = b
+    out["ser_depth"] = np.int64(p.serialized_depth)
+    out["ser_code"] = p.serialized_code.numpy()
+    out["ser_order"] = p.serialized_order.numpy()
+    out["ser_inverse"] = p.serialized_inverse.numpy()
+
+    # padding tables
+    cases = {"a": ([5, 12], 4), "b": ([3, 11], 4), "c": ([8, 9], 4), "d": ([10], 4),
+             "e": ([3000, 5000], 1024), "f": ([100, 1124, 1125, 4000], 1024), "g": ([1024, 2048, 2049], 1024),
+             "h": ([48, 96, 97, 200], 48)}
+    for name, (offset, K) in cases.items():
+        attn = SA(channels=16, num_heads=1, patch_size=K, enable_flash=False, upcast_attention=True, upcast_softmax=True)
+        attn.patch_size = K
+        pt = Point(offset=torch.tensor(offset), feat=torch.zeros(offset[-1], 1))
+        pad, unpad, cu = attn.get_padding_and_inverse(pt)
+        out[f"pad_{name}_offset"] = np.array(offset, dtype=np.int64)
+        out[f"pad_{name}_K"] = np.int64(K)
+        out[f"pad_{name}_pad"] = pad.numpy()
+        out[f"pad_{name}_unpad"] = unpad.numpy()
+        out[f"pad_{name}_cu"] = cu.numpy()
+    np.savez_compressed(os.path.join(OUT, "point_padding.npz"), **out)
+    print("point_padding.npz", len(out), "arrays")
+
+    # dense (non-flash) attention of the reference, fp32, with gradients.
+    # scenes all >= K so the non-flash branch keeps K (ptv3m1:173-176).
+    torch.manual_seed(0)
+    K, C, H = 64, 32, 2
+    offset = [200, 200 + 64, 200 + 64 + 333]
+    N = offset[-1]
+    attn = SA(channels=C, num_heads=H, patch_size=K, enable_flash=False, upcast_attention=True, upcast_softmax=True)
+    gc = torch.from_numpy(np.stack([np.arange(N) % 32, (np.arange(N) // 32) % 32, np.arange(N) // 1024], 1).astype(np.int32))
+    feat = torch.randn(N, C, requires_grad=True)
+    pt = Point(offset=torch.tensor(offset), grid_coord=gc, feat=feat)
+    pt.serialization(order=("z", "hilbert"), shuffle_orders=False)
+    attn.order_index = 1
+    # capture the packed qkv the reference feeds the attention core, and the core's output
+    cap = {}
+    qkv_lin = attn.qkv
+    orig_fwd = qkv_lin.forward
+    def qkv_fwd(x):
+        y = orig_fwd(x)
+        y.retain_grad()
+        cap["qkv_full"] = y
+        return y
+    qkv_lin.forward = qkv_fwd
+    proj_orig = attn.proj.forward
+    def proj_fwd(x):
+        x.retain_grad()
+        cap["core_out_unpadded"] = x
+        return proj_orig(x)
+    attn.proj.forward = proj_fwd
+    res = attn(pt)
+    g = torch.randn_like(res.feat)
+    res.feat.backward(g)
+    pad, unpad, cu = pt["pad"], pt["unpad"], pt["cu_seqlens_key"]
+    np.savez_compressed(
+        os.path.join(OUT, "attention_dense.npz"),
+        offset=np.array(offset), K=np.int64(K), H=np.int64(H), C=np.int64(C),
+        scale=np.float64(attn.scale),
+        order=pt.serialized_order[1].numpy(), inverse=pt.serialized_inverse[1].numpy(),
+        pad=pad.numpy(), unpad=unpad.numpy(), cu=cu.numpy(),
+        qkv_full=cap["qkv_full"].detach().numpy(),            # [N, 3C] before the [order] gather
+        core_out=cap["core_out_unpadded"].detach().numpy(),    # [N, C] after the [inverse] gather
+        d_core_out=cap["core_out_unpadded"].grad.numpy(),
+        d_qkv_full=cap["qkv_full"].grad.numpy(),
+    )
+    print("attention_dense.npz")
+
+
+if __name__ == "__main__":
+    assert ref_import.available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    gen_serialization()
+    gen_point_and_padding()

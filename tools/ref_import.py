@@ -1,0 +1,145 @@
+"""Load the UNMODIFIED reference python files from /root/reference in this container.
+
+Only used by tools/gen_golden.py (fixture generation) and by CPU tests that skip
+when /root/reference is absent (it does not exist on the GPU box).  Third-party
+modules the reference imports but this image lacks are replaced by minimal stand-ins
+for names that are NOT on the hot path (addict.Dict, timm DropPath, torch_scatter,
+HookBase ...); ``spconv`` / ``flash_attn`` can be either stubs or our drop-in shims.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF = os.environ.get("POINTCEPT_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "pointcept"))
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _load(name, relpath):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, relpath))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+class _AttrDict(dict):
+    """stand-in for addict.Dict (attribute access on a dict)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def load_serialization():
+    """-> module with encode(), z_order, hilbert exactly as the reference defines them."""
+    pkg = "_ref_serialization"
+    p = _mod(pkg)
+    p.__path__ = [os.path.join(REF, "pointcept/models/utils/serialization")]
+    _load(pkg + ".z_order", "pointcept/models/utils/serialization/z_order.py")
+    _load(pkg + ".hilbert", "pointcept/models/utils/serialization/hilbert.py")
+    return _load(pkg + ".default", "pointcept/models/utils/serialization/default.py")
+
+
+def load_models(use_shims=False):
+    """Import structure.py, modules.py, PT-v3m1 and SpUNet-v1m1 from the reference.
+
+    use_shims=True wires ``spconv`` / ``flash_attn`` to pointcept_b200's drop-in modules
+    (the boundary test); otherwise inert stubs are used (CPU oracle / golden generation).
+    """
+    import torch
+    import torch.nn as nn
+
+    _mod("addict", Dict=_AttrDict)
+
+    class DropPath(nn.Module):
+        def __init__(self, p=0.0):
+            super().__init__()
+            self.p = p
+
+        def forward(self, x):
+            return x
+
+    _mod("timm")
+    _mod("timm.layers", DropPath=DropPath, trunc_normal_=nn.init.trunc_normal_)
+
+    def segment_csr(src, indptr, reduce="sum"):
+        out = []
+        for a, b in zip(indptr[:-1].tolist(), indptr[1:].tolist()):
+            seg = src[a:b]
+            out.append({"sum": seg.sum(0), "mean": seg.mean(0), "max": seg.max(0).values,
+                        "min": seg.min(0).values}[reduce])
+        return torch.stack(out)
+
+    _mod("torch_scatter", segment_csr=segment_csr)
+    _mod("torch_geometric")
+    _mod("torch_geometric.utils", scatter=None)
+
+    if use_shims:
+        import pointcept_b200
+        pointcept_b200.install(flash_attn=True)
+    else:
+        class _Stub(nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+        sp = _mod("spconv")
+        spt = _mod("spconv.pytorch", SubMConv3d=_Stub, SparseConv3d=_Stub, SparseInverseConv3d=_Stub,
+                   SparseModule=nn.Module, SparseSequential=nn.Sequential, Identity=nn.Identity,
+                   SparseConvTensor=object)
+        spt.modules = _mod("spconv.pytorch.modules", is_spconv_module=lambda m: isinstance(m, _Stub))
+        sp.pytorch = spt
+        sys.modules["flash_attn"] = None  # "import flash_attn" raises ImportError -> reference sets it to None
+
+    # parent packages (empty shells so relative/absolute imports of the files below resolve)
+    for name in ["pointcept", "pointcept.models", "pointcept.models.utils", "pointcept.engines",
+                 "pointcept.models.point_prompt_training", "pointcept.utils"]:
+        if name not in sys.modules:
+            m = _mod(name)
+            m.__path__ = []
+
+    class HookBase:
+        pass
+
+    _mod("pointcept.engines.hooks", HookBase=HookBase)
+
+    class _Registry:
+        def register_module(self, name=None, force=False, module=None):
+            def deco(cls):
+                return cls
+            return deco
+
+    _mod("pointcept.models.builder", MODELS=_Registry(), MODULES=_Registry())
+    _mod("pointcept.models.point_prompt_training", PDNorm=None)
+    ser = "pointcept.models.utils.serialization"
+    sp_ = _mod(ser)
+    sp_.__path__ = [os.path.join(REF, "pointcept/models/utils/serialization")]
+    _load(ser + ".z_order", "pointcept/models/utils/serialization/z_order.py")
+    _load(ser + ".hilbert", "pointcept/models/utils/serialization/hilbert.py")
+    d = _load(ser + ".default", "pointcept/models/utils/serialization/default.py")
+    sp_.encode = d.encode
+    misc = _load("pointcept.models.utils.misc", "pointcept/models/utils/misc.py")
+    u = sys.modules["pointcept.models.utils"]
+    for k in ("offset2batch", "batch2offset", "offset2bincount", "bincount2offset"):
+        setattr(u, k, getattr(misc, k))
+    structure = _load("pointcept.models.utils.structure", "pointcept/models/utils/structure.py")
+    modules = _load("pointcept.models.modules", "pointcept/models/modules.py")
+    ptv3 = _load("pointcept.models.point_transformer_v3.point_transformer_v3m1_base",
+                 "pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py")
+    spunet = _load("pointcept.models.sparse_unet.spconv_unet_v1m1_base",
+                   "pointcept/models/sparse_unet/spconv_unet_v1m1_base.py")
+    return types.SimpleNamespace(structure=structure, modules=modules, ptv3=ptv3, spunet=spunet, misc=misc)

@@ -1,0 +1,148 @@
+/*
+ * b2pc.h -- C ABI of libb2pc.so, the B200 (sm_100a) point-cloud backbone operator library.
+ *
+ * This is the drop-in boundary for the two third-party operator packages Pointcept's
+ * PT-v3m1 / SpUNet-v1m1 hot path calls (the reference itself has no C ABI: its in-repo
+ * extensions bind at::Tensor through pybind11, e.g. libs/pointops/src/pointops_api.cpp:15-32,
+ * and the hot-path arithmetic lives in the spconv / flash-attn wheels).  Each entry point
+ * names the reference call site it serves.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative b2pc_status; b2pc_last_error()
+ *     returns a thread-local message for the last failure on the calling thread;
+ *   - all data pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - functions never allocate, free or synchronise: the caller owns every buffer, passes
+ *     scratch memory obtained from the matching *_workspace_bytes() query, and passes the
+ *     CUDA stream to launch on (cudaStream_t == b2pc_stream_t);
+ *   - re-entrant and thread-safe (forward on the main thread, backward on autograd's
+ *     device thread; one process per GPU as in pointcept/engines/launch.py:73);
+ *   - dtype enum: 0 = fp32, 1 = fp16, 2 = bf16 (features/weights; accumulation is fp32).
+ */
+#ifndef B2PC_H_
+#define B2PC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b2pc_stream_t;
+
+typedef enum {
+  B2PC_OK = 0,
+  B2PC_ERR_INVALID_ARG = -1,
+  B2PC_ERR_WORKSPACE = -2,
+  B2PC_ERR_CUDA = -3,
+  B2PC_ERR_UNSUPPORTED = -4
+} b2pc_status;
+
+enum { B2PC_F32 = 0, B2PC_F16 = 1, B2PC_BF16 = 2 };
+/* serialization orders, pointcept/models/utils/serialization/default.py:10-18 */
+enum { B2PC_ORDER_Z = 0, B2PC_ORDER_Z_TRANS = 1, B2PC_ORDER_HILBERT = 2, B2PC_ORDER_HILBERT_TRANS = 3 };
+
+int b2pc_version(void);
+const char* b2pc_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Serialization: replaces encode() (serialization/default.py:9-24, z_order.py:66-101,
+ * hilbert.py:91-192) and the argsort / inverse scatter of Point.serialization
+ * (models/utils/structure.py:85-100).
+ * ------------------------------------------------------------------------------------------- */
+
+/* code[o, i] = (batch[i] << 3*depth) | curve_{orders_host[o]}(grid_coord[i]);  all requested
+ * orders in one pass over the coordinates.  grid_coord [N,3] int32, batch [N] int64 or NULL,
+ * code [n_orders, N] int64.  1 <= depth <= 16, n_orders <= 8. */
+int b2pc_serialize_encode(const int32_t* grid_coord, const int64_t* batch, int64_t n, int depth,
+                          const int* orders_host, int n_orders, int64_t* code, b2pc_stream_t stream);
+
+size_t b2pc_serialize_sort_workspace_bytes(int64_t n, int n_orders);
+/* Stable LSD radix sort of every row of code[n_orders, N] on its low key_bits bits
+ * (key_bits = 3*depth + bits(batch_size-1); <= 63).  order[o] = argsort(code[o]) (int64, as
+ * torch.argsort returns), inverse[o][order[o][i]] = i.  Only the significant bits are sorted. */
+int b2pc_serialize_sort(const int64_t* code, int64_t n, int n_orders, int key_bits, int64_t* order,
+                        int64_t* inverse, void* workspace, size_t workspace_bytes,
+                        b2pc_stream_t stream);
+
+/* Patch padding tables: replaces SerializedAttention.get_padding_and_inverse
+ * (point_transformer_v3/point_transformer_v3m1_base.py:114-170) without its per-scene host loop.
+ * offset [B] int64 (device, cumulative scene sizes).  The caller knows the scene sizes on the
+ * host and passes t_pad = sum of padded sizes and n_seq = number of patches.
+ * pad [t_pad] int64, unpad [n] int64, cu_seqlens [n_seq+1] int32. */
+int b2pc_patch_padding(const int64_t* offset, int batch_size, int patch_size, int64_t n, int64_t t_pad,
+                       int n_seq, int64_t* pad, int64_t* unpad, int32_t* cu_seqlens,
+                       b2pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch attention: replaces flash_attn.flash_attn_varlen_qkvpacked_func as called at
+ * point_transformer_v3m1_base.py:208-214 (non-causal, no dropout, no mask).
+ * qkv [T,3,H,D] contiguous (fp16 or bf16), cu_seqlens [n_seq+1] int32, out [T,H,D] (same dtype),
+ * lse [H,T] fp32 (natural-log sum-exp of scale*QK^T, flash-attn's softmax_lse layout).
+ * impl: 0 = auto (tcgen05 kernel when the shape is supported), 1 = SIMT reference kernel,
+ *       2 = tcgen05 kernel (error if unsupported).
+ * ------------------------------------------------------------------------------------------- */
+int b2pc_patch_attn_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int n_seq, int max_seqlen,
+                        int64_t t, int heads, int head_dim, float scale, void* out, float* lse,
+                        int impl, b2pc_stream_t stream);
+
+size_t b2pc_patch_attn_bwd_workspace_bytes(int64_t t, int heads, int head_dim);
+/* dqkv [T,3,H,D] (same dtype) from dout [T,H,D], the forward's qkv / out / lse. */
+int b2pc_patch_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse, int dtype,
+                        const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t, int heads,
+                        int head_dim, float scale, void* dqkv, void* workspace, size_t workspace_bytes,
+                        int impl, b2pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse convolution rulebooks: replaces the indice-pair generation inside
+ * spconv.pytorch.SubMConv3d / SparseConv3d (call sites: point_transformer_v3m1_base.py:278-284,
+ * 499-506; sparse_unet/spconv_unet_v1m1_base.py:43-68,114-121,137-144,173-179,222-224).
+ * indices [N,4] int32 rows (b, x, y, z) as built at models/utils/structure.py:139-146.
+ * Rulebook form: pair[KV, N_out] int32, entry = input row feeding output row j through kernel
+ * offset k = (i0*K1+i1)*K2+i2, or -1.
+ * ------------------------------------------------------------------------------------------- */
+size_t b2pc_rulebook_workspace_bytes(int64_t n, int kv);
+/* Submanifold: output set == input set (same rows); padding is implied (K//2 * dilation). */
+int b2pc_rulebook_subm(const int32_t* indices, int64_t n, const int* spatial_shape_host,
+                       const int* ksize_host, const int* dilation_host, int32_t* pair,
+                       void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
+/* Strided (SparseConv3d): out coordinate o is active iff some input i and offset k satisfy
+ * i = o*stride - padding + k*dilation.  Output rows are the distinct out coordinates in
+ * ascending (b,x,y,z) order.  out_indices [cap,4], pair_fwd [KV,cap] (row stride = cap),
+ * pair_bwd [KV,N]; *num_out (device int64) receives M <= cap.  Stage 1 of 2: counts the
+ * distinct outputs; the caller reads *num_out (one host sync, as spconv does) and calls
+ * b2pc_rulebook_strided_finish with it. */
+int b2pc_rulebook_strided_begin(const int32_t* indices, int64_t n, const int* spatial_shape_host,
+                                const int* ksize_host, const int* stride_host, const int* padding_host,
+                                const int* dilation_host, int64_t* num_out, void* workspace,
+                                size_t workspace_bytes, b2pc_stream_t stream);
+int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* spatial_shape_host,
+                                 const int* ksize_host, const int* stride_host, const int* padding_host,
+                                 const int* dilation_host, int64_t num_out_host, int32_t* out_indices,
+                                 int32_t* pair_fwd, int32_t* pair_bwd, void* workspace,
+                                 size_t workspace_bytes, b2pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse convolution arithmetic (gather - GEMM - accumulate, output stationary, no atomics):
+ *   out[j, :] = bias + sum_k  in[pair[k', j], :] @ W_k          k' = flip ? KV-1-k : k
+ * Forward:        W_k = weight[:, k, :]^T   (weight [Cout, KV, Cin], the spconv parameter layout)
+ * Backward data:  same routine on dout with transpose_w = 1 (W_k = weight[:, k, :], [Cout]->[Cin]);
+ *                 SubM passes the forward table with flip = 1 (the table is its own inverse under
+ *                 k -> KV-1-k), strided / inverse convs pass the opposite-direction table.
+ * n_in rows of feat, n_out rows of out / columns of pair.  impl as for attention.
+ * ------------------------------------------------------------------------------------------- */
+int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bias, const int32_t* pair,
+                            int64_t pair_stride, int64_t n_in, int64_t n_out, int c_in, int c_out, int kv,
+                            int transpose_w, int flip, int dtype, void* out, int impl, b2pc_stream_t stream);
+
+size_t b2pc_spconv_bwd_weight_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv);
+/* dweight[co, k, ci] = sum_j  dout[j, co] * feat_in[pair[k, j], ci]   (fp32 result, deterministic). */
+int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t* pair, int64_t pair_stride,
+                           int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int dtype,
+                           float* dweight, void* workspace, size_t workspace_bytes, int impl,
+                           b2pc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2PC_H_ */

@@ -1,0 +1,167 @@
+// libb2pc.so -- C ABI (include/b2pc.h) over the sm_100a kernels.  No torch types cross this boundary.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "serialize.cuh"
+#include "sort.cuh"
+#include "rulebook.cuh"
+#include "spconv_simt.cuh"
+#include "attn_simt.cuh"
+#ifndef B2PC_NO_UMMA
+#include "spconv_umma.cuh"
+#include "attn_umma.cuh"
+#endif
+
+namespace b2pc {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace b2pc
+
+using namespace b2pc;
+
+extern "C" {
+
+int b2pc_version(void) { return 100; }
+const char* b2pc_last_error(void) { return g_err; }
+
+int b2pc_serialize_encode(const int32_t* grid_coord, const int64_t* batch, int64_t n, int depth, const int* orders_host,
+                          int n_orders, int64_t* code, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(grid_coord && code && orders_host, "serialize_encode: null pointer");
+  return launch_encode(grid_coord, batch, n, depth, orders_host, n_orders, code, (cudaStream_t)stream);
+}
+
+size_t b2pc_serialize_sort_workspace_bytes(int64_t n, int n_orders) { return sort_workspace_bytes(n, n_orders); }
+
+int b2pc_serialize_sort(const int64_t* code, int64_t n, int n_orders, int key_bits, int64_t* order, int64_t* inverse,
+                        void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(code && order && inverse && workspace, "serialize_sort: null pointer");
+  return launch_sort(code, n, n_orders, key_bits, order, inverse, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b2pc_patch_padding(const int64_t* offset, int batch_size, int patch_size, int64_t n, int64_t t_pad, int n_seq,
+                       int64_t* pad, int64_t* unpad, int32_t* cu_seqlens, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(offset && pad && unpad && cu_seqlens, "patch_padding: null pointer");
+  return launch_padding(offset, batch_size, patch_size, n, t_pad, n_seq, pad, unpad, cu_seqlens, (cudaStream_t)stream);
+}
+
+// ---- attention ------------------------------------------------------------------------------------
+int b2pc_patch_attn_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t,
+                        int heads, int head_dim, float scale, void* out, float* lse, int impl, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(qkv && cu_seqlens && out && lse, "patch_attn_fwd: null pointer");
+  B2PC_CHECK_ARG(dtype == B2PC_F16 || dtype == B2PC_BF16, "patch_attn_fwd: dtype must be fp16 or bf16 (got %d)", dtype);
+  B2PC_CHECK_ARG(n_seq >= 0 && max_seqlen >= 0 && t >= 0 && heads > 0 && head_dim > 0, "patch_attn_fwd: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+#ifndef B2PC_NO_UMMA
+  if (impl != 1) {
+    if (attn_umma_supported(dtype, head_dim)) return launch_attn_fwd_umma(qkv, dtype, cu_seqlens, n_seq, max_seqlen, t, heads, head_dim, scale, out, lse, s);
+    if (impl == 2) { set_error("patch_attn_fwd: tcgen05 kernel does not support dtype %d head_dim %d", dtype, head_dim); return B2PC_ERR_UNSUPPORTED; }
+  }
+#else
+  if (impl == 2) { set_error("patch_attn_fwd: built without tcgen05 kernels"); return B2PC_ERR_UNSUPPORTED; }
+#endif
+  if (dtype == B2PC_F16) return launch_attn_fwd_simt<__half>(qkv, cu_seqlens, n_seq, max_seqlen, t, heads, head_dim, scale, out, lse, s);
+  return launch_attn_fwd_simt<__nv_bfloat16>(qkv, cu_seqlens, n_seq, max_seqlen, t, heads, head_dim, scale, out, lse, s);
+}
+
+size_t b2pc_patch_attn_bwd_workspace_bytes(int64_t t, int heads, int head_dim) {
+  size_t b = attn_bwd_workspace_bytes(t, heads, head_dim);
+#ifndef B2PC_NO_UMMA
+  size_t u = attn_bwd_umma_workspace_bytes(t, heads, head_dim);
+  if (u > b) b = u;
+#endif
+  return b;
+}
+
+int b2pc_patch_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse, int dtype,
+                        const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t, int heads, int head_dim,
+                        float scale, void* dqkv, void* workspace, size_t workspace_bytes, int impl, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(dout && qkv && out && lse && cu_seqlens && dqkv && workspace, "patch_attn_bwd: null pointer");
+  B2PC_CHECK_ARG(dtype == B2PC_F16 || dtype == B2PC_BF16, "patch_attn_bwd: dtype must be fp16 or bf16 (got %d)", dtype);
+  if (workspace_bytes < b2pc_patch_attn_bwd_workspace_bytes(t, heads, head_dim)) { set_error("patch_attn_bwd: workspace too small"); return B2PC_ERR_WORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+#ifndef B2PC_NO_UMMA
+  if (impl != 1) {
+    if (attn_umma_supported(dtype, head_dim)) return launch_attn_bwd_umma(dout, qkv, out, lse, dtype, cu_seqlens, n_seq, max_seqlen, t, heads, head_dim, scale, dqkv, workspace, s);
+    if (impl == 2) { set_error("patch_attn_bwd: tcgen05 kernel does not support dtype %d head_dim %d", dtype, head_dim); return B2PC_ERR_UNSUPPORTED; }
+  }
+#else
+  if (impl == 2) { set_error("patch_attn_bwd: built without tcgen05 kernels"); return B2PC_ERR_UNSUPPORTED; }
+#endif
+  if (dtype == B2PC_F16) return launch_attn_bwd_simt<__half>(dout, qkv, out, lse, cu_seqlens, n_seq, max_seqlen, t, heads, head_dim, scale, dqkv, workspace, s);
+  return launch_attn_bwd_simt<__nv_bfloat16>(dout, qkv, out, lse, cu_seqlens, n_seq, max_seqlen, t, heads, head_dim, scale, dqkv, workspace, s);
+}
+
+// ---- rulebooks --------------------------------------------------------------------------------------
+size_t b2pc_rulebook_workspace_bytes(int64_t n, int kv) { return rulebook_workspace_bytes(n, kv); }
+
+int b2pc_rulebook_subm(const int32_t* indices, int64_t n, const int* spatial_shape_host, const int* ksize_host,
+                       const int* dilation_host, int32_t* pair, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(indices && spatial_shape_host && ksize_host && pair && workspace, "rulebook_subm: null pointer");
+  return launch_rulebook_subm(indices, n, spatial_shape_host, ksize_host, dilation_host, pair, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b2pc_rulebook_strided_begin(const int32_t* indices, int64_t n, const int* spatial_shape_host, const int* ksize_host,
+                                const int* stride_host, const int* padding_host, const int* dilation_host, int64_t* num_out,
+                                void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(indices && spatial_shape_host && ksize_host && num_out && workspace, "rulebook_strided_begin: null pointer");
+  return launch_rulebook_strided_begin(indices, n, spatial_shape_host, ksize_host, stride_host, padding_host, dilation_host, num_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* spatial_shape_host, const int* ksize_host,
+                                 const int* stride_host, const int* padding_host, const int* dilation_host, int64_t num_out_host,
+                                 int32_t* out_indices, int32_t* pair_fwd, int32_t* pair_bwd, void* workspace, size_t workspace_bytes,
+                                 b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(indices && spatial_shape_host && ksize_host && out_indices && pair_fwd && pair_bwd && workspace, "rulebook_strided_finish: null pointer");
+  return launch_rulebook_strided_finish(indices, n, spatial_shape_host, ksize_host, stride_host, padding_host, dilation_host, num_out_host, out_indices, pair_fwd, pair_bwd, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- sparse convolution arithmetic ---------------------------------------------------------------------
+int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bias, const int32_t* pair, int64_t pair_stride,
+                            int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, int dtype,
+                            void* out, int impl, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(feat && weight && pair && out, "spconv_gather_gemm: null pointer");
+  B2PC_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && kv > 0 && pair_stride >= n_out, "spconv_gather_gemm: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+#ifndef B2PC_NO_UMMA
+  if (impl != 1) {
+    if (spconv_umma_supported(dtype, c_in, c_out)) return launch_gather_gemm_umma(feat, weight, bias, pair, pair_stride, n_in, n_out, c_in, c_out, kv, transpose_w, flip, dtype, out, s);
+    if (impl == 2) { set_error("spconv_gather_gemm: tcgen05 kernel does not support dtype %d c_in %d c_out %d", dtype, c_in, c_out); return B2PC_ERR_UNSUPPORTED; }
+  }
+#else
+  if (impl == 2) { set_error("spconv_gather_gemm: built without tcgen05 kernels"); return B2PC_ERR_UNSUPPORTED; }
+#endif
+  switch (dtype) {
+    case B2PC_F32: return launch_gather_gemm_simt<float>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, s);
+    case B2PC_F16: return launch_gather_gemm_simt<__half>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, s);
+    case B2PC_BF16: return launch_gather_gemm_simt<__nv_bfloat16>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, s);
+  }
+  set_error("spconv_gather_gemm: unknown dtype %d", dtype);
+  return B2PC_ERR_INVALID_ARG;
+}
+
+size_t b2pc_spconv_bwd_weight_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
+  return bwd_weight_workspace_bytes(n_out, c_in, c_out, kv);
+}
+
+int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t* pair, int64_t pair_stride, int64_t n_in,
+                           int64_t n_out, int c_in, int c_out, int kv, int dtype, float* dweight, void* workspace,
+                           size_t workspace_bytes, int impl, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(feat_in && dout && pair && dweight && workspace, "spconv_bwd_weight: null pointer");
+  B2PC_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && kv > 0 && pair_stride >= n_out, "spconv_bwd_weight: bad sizes");
+  (void)impl;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case B2PC_F32: return launch_bwd_weight_simt<float>(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dweight, workspace, workspace_bytes, s);
+    case B2PC_F16: return launch_bwd_weight_simt<__half>(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dweight, workspace, workspace_bytes, s);
+    case B2PC_BF16: return launch_bwd_weight_simt<__nv_bfloat16>(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dweight, workspace, workspace_bytes, s);
+  }
+  set_error("spconv_bwd_weight: unknown dtype %d", dtype);
+  return B2PC_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+"""torch-tensor front end of the C ABI (include/b2pc.h): allocation, stream plumbing and autograd.
+
+Every function requires CUDA tensors and raises otherwise -- there is no CPU / eager fallback.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+ORDER_IDS = {"z": 0, "z-trans": 1, "hilbert": 2, "hilbert-trans": 3}
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+# 0 = auto (tcgen05 kernels where supported), 1 = SIMT reference kernels, 2 = tcgen05 or error
+_impl = int(os.environ.get("B2PC_IMPL", "0"))
+
+
+def set_impl(v):
+    global _impl
+    _impl = int(v)
+
+
+def get_impl():
+    return _impl
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pointcept_b200 operators run on CUDA tensors only (got a %s tensor); "
+                               "there is no CPU fallback" % t.device.type)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def _i3(v):
+    v = (v, v, v) if isinstance(v, int) else tuple(int(x) for x in v)
+    assert len(v) == 3
+    return (ctypes.c_int * 3)(*v), v
+
+
+# ------------------------------------------------------------------------------------------------
+# serialization
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def serialize_encode(grid_coord, batch, depth, orders):
+    """codes [len(orders), N] int64; all orders in one kernel (serialization/default.py:9-24)."""
+    _need_cuda(grid_coord, batch)
+    gc = grid_coord if (grid_coord.dtype == torch.int32 and grid_coord.is_contiguous()) else grid_coord.int().contiguous()
+    if batch is not None and (batch.dtype != torch.int64 or not batch.is_contiguous()):
+        batch = batch.long().contiguous()
+    n = gc.shape[0]
+    ids = (ctypes.c_int * len(orders))(*[ORDER_IDS[o] for o in orders])
+    code = torch.empty((len(orders), n), dtype=torch.int64, device=gc.device)
+    L = _lib.lib()
+    _lib.check(L.b2pc_serialize_encode(_p(gc), _p(batch), n, int(depth), ids, len(orders), _p(code), _stream()), "serialize_encode")
+    return code
+
+
+@torch.no_grad()
+def serialize_sort(code, key_bits):
+    """order, inverse [k, N] int64 for code [k, N] int64 (structure.py:93-100)."""
+    _need_cuda(code)
+    code = code.contiguous()
+    k, n = code.shape
+    order = torch.empty_like(code)
+    inverse = torch.empty_like(code)
+    L = _lib.lib()
+    ws = _ws(L.b2pc_serialize_sort_workspace_bytes(n, k), code.device)
+    _lib.check(L.b2pc_serialize_sort(_p(code), n, k, int(key_bits), _p(order), _p(inverse), _p(ws), ws.numel(), _stream()),
+               "serialize_sort")
+    return order, inverse
+
+
+@torch.no_grad()
+def patch_padding(offset, offset_host, patch_size):
+    """pad, unpad, cu_seqlens as SerializedAttention.get_padding_and_inverse (ptv3m1:114-170).
+
+    offset: device int64 [B]; offset_host: the same values on the host (list of ints)."""
+    _need_cuda(offset)
+    K = int(patch_size)
+    counts = [b - a for a, b in zip([0] + list(offset_host[:-1]), offset_host)]
+    padded = [((c + K - 1) // K * K) if c > K else c for c in counts]
+    n, t_pad = int(offset_host[-1]), sum(padded)
+    n_seq = sum(((c + K - 1) // K) if c > 0 else 0 for c in padded)
+    dev = offset.device
+    pad = torch.empty(t_pad, dtype=torch.int64, device=dev)
+    unpad = torch.empty(n, dtype=torch.int64, device=dev)
+    cu = torch.empty(n_seq + 1, dtype=torch.int32, device=dev)
+    off = offset if offset.dtype == torch.int64 else offset.long()
+    L = _lib.lib()
+    _lib.check(L.b2pc_patch_padding(_p(off.contiguous()), len(offset_host), K, n, t_pad, n_seq, _p(pad), _p(unpad), _p(cu), _stream()),
+               "patch_padding")
+    return pad, unpad, cu
+
+
+# ------------------------------------------------------------------------------------------------
+# patch attention
+# ------------------------------------------------------------------------------------------------
+class PatchAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, cu_seqlens, max_seqlen, scale):
+        _need_cuda(qkv, cu_seqlens)
+        if qkv.dtype not in (torch.float16, torch.bfloat16):
+            raise RuntimeError("patch attention takes fp16 or bf16 qkv (flash-attn contract), got %s" % qkv.dtype)
+        qkv = qkv.contiguous()
+        T, three, H, D = qkv.shape
+        assert three == 3
+        cu = cu_seqlens if cu_seqlens.dtype == torch.int32 else cu_seqlens.int()
+        cu = cu.contiguous()
+        out = torch.empty((T, H, D), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((H, T), dtype=torch.float32, device=qkv.device)
+        L = _lib.lib()
+        _lib.check(L.b2pc_patch_attn_fwd(_p(qkv), _DTYPES[qkv.dtype], _p(cu), cu.numel() - 1, int(max_seqlen), T, H, D,
+                                         float(scale), _p(out), _p(lse), _impl, _stream()), "patch_attn_fwd")
+        ctx.save_for_backward(qkv, out, lse, cu)
+        ctx.max_seqlen, ctx.scale = int(max_seqlen), float(scale)
+        ctx.mark_non_differentiable(lse)
+        return out, lse
+
+    @staticmethod
+    def backward(ctx, dout, _dlse):
+        qkv, out, lse, cu = ctx.saved_tensors
+        T, _, H, D = qkv.shape
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        L = _lib.lib()
+        ws = _ws(L.b2pc_patch_attn_bwd_workspace_bytes(T, H, D), qkv.device)
+        _lib.check(L.b2pc_patch_attn_bwd(_p(dout), _p(qkv), _p(out), _p(lse), _DTYPES[qkv.dtype], _p(cu), cu.numel() - 1,
+                                         ctx.max_seqlen, T, H, D, ctx.scale, _p(dqkv), _p(ws), ws.numel(), _impl, _stream()),
+                   "patch_attn_bwd")
+        return dqkv, None, None, None
+
+
+def patch_attention(qkv, cu_seqlens, max_seqlen, scale=None, return_lse=False):
+    if scale is None:
+        scale = qkv.shape[-1] ** -0.5
+    out, lse = PatchAttentionFn.apply(qkv, cu_seqlens, max_seqlen, scale)
+    return (out, lse) if return_lse else out
+
+
+# ------------------------------------------------------------------------------------------------
+# rulebooks
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def rulebook_subm(indices, spatial_shape, ksize, dilation=1):
+    """pair [KV, N] int32 (input row or -1) for a submanifold convolution."""
+    _need_cuda(indices)
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4
+    indices = indices.contiguous()
+    n = indices.shape[0]
+    shp, _ = _i3(list(spatial_shape))
+    ks, kt = _i3(ksize)
+    dl, _ = _i3(dilation)
+    kv = kt[0] * kt[1] * kt[2]
+    pair = torch.empty((kv, n), dtype=torch.int32, device=indices.device)
+    L = _lib.lib()
+    ws = _ws(L.b2pc_rulebook_workspace_bytes(n, 1), indices.device)
+    _lib.check(L.b2pc_rulebook_subm(_p(indices), n, shp, ks, dl, _p(pair), _p(ws), ws.numel(), _stream()), "rulebook_subm")
+    return pair
+
+
+@torch.no_grad()
+def rulebook_strided(indices, spatial_shape, ksize, stride, padding=0, dilation=1):
+    """-> out_indices [M,4] int32 (ascending (b,x,y,z)), out_shape, pair_fwd [KV,M], pair_bwd [KV,N].
+    One host sync to learn M (as spconv does)."""
+    _need_cuda(indices)
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4
+    indices = indices.contiguous()
+    n = indices.shape[0]
+    shp, shape_t = _i3(list(spatial_shape))
+    ks, kt = _i3(ksize)
+    st, stt = _i3(stride)
+    pd, pdt = _i3(padding)
+    dl, dlt = _i3(dilation)
+    kv = kt[0] * kt[1] * kt[2]
+    out_shape = [(shape_t[a] + 2 * pdt[a] - dlt[a] * (kt[a] - 1) - 1) // stt[a] + 1 for a in range(3)]
+    L = _lib.lib()
+    dev = indices.device
+    ws = _ws(L.b2pc_rulebook_workspace_bytes(n, kv), dev)
+    num = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.check(L.b2pc_rulebook_strided_begin(_p(indices), n, shp, ks, st, pd, dl, _p(num), _p(ws), ws.numel(), _stream()),
+               "rulebook_strided_begin")
+    m = int(num.item())
+    out_indices = torch.empty((m, 4), dtype=torch.int32, device=dev)
+    pair_fwd = torch.empty((kv, m), dtype=torch.int32, device=dev)
+    pair_bwd = torch.empty((kv, n), dtype=torch.int32, device=dev)
+    _lib.check(L.b2pc_rulebook_strided_finish(_p(indices), n, shp, ks, st, pd, dl, m, _p(out_indices), _p(pair_fwd), _p(pair_bwd),
+                                              _p(ws), ws.numel(), _stream()), "rulebook_strided_finish")
+    return out_indices, out_shape, pair_fwd, pair_bwd
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse convolution arithmetic
+# ------------------------------------------------------------------------------------------------
+def _gather_gemm(feat, weight, bias, pair, n_out, c_in, c_out, kv, transpose_w, flip):
+    out = torch.empty((n_out, c_out), dtype=feat.dtype, device=feat.device)
+    L = _lib.lib()
+    _lib.check(L.b2pc_spconv_gather_gemm(_p(feat), _p(weight), _p(bias), _p(pair), pair.shape[1], feat.shape[0], n_out, c_in, c_out,
+                                         kv, int(transpose_w), int(flip), _DTYPES[feat.dtype], _p(out), _impl, _stream()),
+               "spconv_gather_gemm")
+    return out
+
+
+class SparseConvFn(torch.autograd.Function):
+    """out = bias + sum_k feat[table_fwd[k]] @ weight[:, k, :].T
+
+    feat [N_in, Cin] (fp32/fp16/bf16); weight [Cout, KV, Cin] fp32 master parameter (cast to feat's dtype
+    inside, its gradient is produced in fp32); table_fwd [KV, N_out]; table_bwd [KV, N_in] is the rulebook
+    of the opposite direction (SubM: the same table read with flipped offsets)."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, table_fwd, table_bwd, flip_bwd):
+        _need_cuda(feat, weight, table_fwd)
+        if feat.dtype not in _DTYPES:
+            raise RuntimeError("sparse conv features must be fp32/fp16/bf16, got %s" % feat.dtype)
+        feat = feat.contiguous()
+        c_out, kv, c_in = weight.shape
+        assert feat.shape[1] == c_in, (feat.shape, weight.shape)
+        w = weight.detach().to(feat.dtype).contiguous()
+        b = bias.detach().to(feat.dtype).contiguous() if bias is not None else None
+        n_out = table_fwd.shape[1]
+        out = _gather_gemm(feat, w, b, table_fwd, n_out, c_in, c_out, kv, False, False)
+        ctx.save_for_backward(feat, w, table_fwd, table_bwd)
+        ctx.flip_bwd = bool(flip_bwd)
+        ctx.has_bias = bias is not None
+        ctx.wdtype = weight.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, w, table_fwd, table_bwd = ctx.saved_tensors
+        c_out, kv, c_in = w.shape
+        dout = dout.contiguous()
+        if dout.dtype != feat.dtype:
+            dout = dout.to(feat.dtype)
+        dfeat = dweight = dbias = None
+        if ctx.needs_input_grad[0]:
+            dfeat = _gather_gemm(dout, w, None, table_bwd, feat.shape[0], c_out, c_in, kv, True, ctx.flip_bwd)
+        if ctx.needs_input_grad[1]:
+            dweight = torch.empty((c_out, kv, c_in), dtype=torch.float32, device=feat.device)
+            L = _lib.lib()
+            n_out = table_fwd.shape[1]
+            ws = _ws(L.b2pc_spconv_bwd_weight_workspace_bytes(n_out, c_in, c_out, kv), feat.device)
+            _lib.check(L.b2pc_spconv_bwd_weight(_p(feat), _p(dout), _p(table_fwd), table_fwd.shape[1], feat.shape[0], n_out, c_in,
+                                                c_out, kv, _DTYPES[feat.dtype], _p(dweight), _p(ws), ws.numel(), _impl, _stream()),
+                       "spconv_bwd_weight")
+            if ctx.wdtype != torch.float32:
+                dweight = dweight.to(ctx.wdtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dbias = dout.float().sum(0)
+        return dfeat, dweight, dbias, None, None, None
+
+
+def sparse_conv(feat, weight, bias, table_fwd, table_bwd, flip_bwd):
+    return SparseConvFn.apply(feat, weight, bias, table_fwd, table_bwd, flip_bwd)

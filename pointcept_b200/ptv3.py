@@ -1,0 +1,361 @@
+"""PT-v3m1 backbone on the B200 operators: host-side mirror of
+pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py (module tree, parameter names and
+shapes identical, so reference checkpoints load), used as the workload of bench.py and the parity tests.
+
+Differences in HOW (not WHAT): serialization / padding tables / attention / CPE convolutions are the
+libb2pc kernels; the padding tables and gather indices are built once per stage on the device without
+the reference's per-scene python loop; pooling clusters come from the already-sorted order-0 codes
+instead of torch.unique + torch.sort.
+"""
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .flash_attn_interface import flash_attn_varlen_qkvpacked_func
+from .spconv import pytorch as spconv
+from .structure import Point, PointModule, PointSequential
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per row (timm.layers.DropPath semantics, as used at ptv3m1:313-315)."""
+
+    def __init__(self, drop_prob=0.0, scale_by_keep=True):
+        super().__init__()
+        self.drop_prob, self.scale_by_keep = drop_prob, scale_by_keep
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            mask.div_(keep)
+        return x * mask
+
+
+class SerializedAttention(PointModule):
+    """ptv3m1:51-222 (flash branch only: RPE / upcast options belong to the non-flash fallback)."""
+
+    def __init__(self, channels, num_heads, patch_size, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0,
+                 order_index=0, enable_rpe=False, enable_flash=True, upcast_attention=False, upcast_softmax=False):
+        super().__init__()
+        assert channels % num_heads == 0
+        if not enable_flash or enable_rpe or upcast_attention or upcast_softmax:
+            raise NotImplementedError("pointcept_b200 implements the enable_flash=True attention path only")
+        if attn_drop != 0.0:
+            raise NotImplementedError("attn_drop > 0 is not supported (all PT-v3 configs use 0.0)")
+        self.channels, self.num_heads = channels, num_heads
+        self.scale = qk_scale or (channels // num_heads) ** -0.5
+        self.order_index = order_index
+        self.patch_size = patch_size
+        self.qkv = nn.Linear(channels, channels * 3, bias=qkv_bias)
+        self.proj = nn.Linear(channels, channels)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    @torch.no_grad()
+    def get_padding_and_inverse(self, point):
+        if "pad" not in point or "unpad" not in point or "cu_seqlens_key" not in point:
+            pad, unpad, cu = ops.patch_padding(point.offset, point.host_offset(), self.patch_size)
+            point["pad"], point["unpad"], point["cu_seqlens_key"] = pad, unpad, cu
+        return point["pad"], point["unpad"], point["cu_seqlens_key"]
+
+    @torch.no_grad()
+    def _gather_indices(self, point):
+        key = f"_attn_idx_{self.order_index}"
+        if key not in point:
+            pad, unpad, _ = self.get_padding_and_inverse(point)
+            point[key] = (point.serialized_order[self.order_index][pad], unpad[point.serialized_inverse[self.order_index]])
+        return point[key]
+
+    def forward(self, point):
+        H, K, C = self.num_heads, self.patch_size, self.channels
+        _, _, cu_seqlens = self.get_padding_and_inverse(point)
+        order, inverse = self._gather_indices(point)
+        qkv = self.qkv(point.feat)[order]
+        feat = flash_attn_varlen_qkvpacked_func(qkv.to(torch.bfloat16).reshape(-1, 3, H, C // H), cu_seqlens, max_seqlen=K,
+                                                softmax_scale=self.scale).reshape(-1, C)
+        feat = feat.to(qkv.dtype)[inverse]
+        point.feat = self.proj_drop(self.proj(feat))
+        return point
+
+
+class MLP(nn.Module):
+    def __init__(self, in_channels, hidden_channels=None, out_channels=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_channels = out_channels or in_channels
+        hidden_channels = hidden_channels or in_channels
+        self.fc1 = nn.Linear(in_channels, hidden_channels)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_channels, out_channels)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+
+
+class Block(PointModule):
+    """ptv3m1:251-338: CPE (SubMConv3d k3 -> Linear -> LN) + attention + MLP, pre- or post-norm."""
+
+    def __init__(self, channels, num_heads, patch_size=48, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, attn_drop=0.0,
+                 proj_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, act_layer=nn.GELU, pre_norm=True, order_index=0,
+                 cpe_indice_key=None, enable_rpe=False, enable_flash=True, upcast_attention=False, upcast_softmax=False):
+        super().__init__()
+        self.channels, self.pre_norm = channels, pre_norm
+        self.cpe = PointSequential(
+            spconv.SubMConv3d(channels, channels, kernel_size=3, bias=True, indice_key=cpe_indice_key),
+            nn.Linear(channels, channels),
+            norm_layer(channels),
+        )
+        self.norm1 = PointSequential(norm_layer(channels))
+        self.attn = SerializedAttention(channels=channels, patch_size=patch_size, num_heads=num_heads, qkv_bias=qkv_bias,
+                                        qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=proj_drop, order_index=order_index,
+                                        enable_rpe=enable_rpe, enable_flash=enable_flash, upcast_attention=upcast_attention,
+                                        upcast_softmax=upcast_softmax)
+        self.norm2 = PointSequential(norm_layer(channels))
+        self.mlp = PointSequential(MLP(in_channels=channels, hidden_channels=int(channels * mlp_ratio), out_channels=channels,
+                                       act_layer=act_layer, drop=proj_drop))
+        self.drop_path = PointSequential(DropPath(drop_path) if drop_path > 0.0 else nn.Identity())
+
+    def forward(self, point):
+        shortcut = point.feat
+        point = self.cpe(point)
+        point.feat = shortcut + point.feat
+        shortcut = point.feat
+        if self.pre_norm:
+            point = self.norm1(point)
+        point = self.drop_path(self.attn(point))
+        point.feat = shortcut + point.feat
+        if not self.pre_norm:
+            point = self.norm1(point)
+        shortcut = point.feat
+        if self.pre_norm:
+            point = self.norm2(point)
+        point = self.drop_path(self.mlp(point))
+        point.feat = shortcut + point.feat
+        if not self.pre_norm:
+            point = self.norm2(point)
+        point.sparse_conv_feat = point.sparse_conv_feat.replace_feature(point.feat)
+        return point
+
+
+class SerializedPooling(PointModule):
+    """ptv3m1:341-444.  Clusters = runs of equal (code >> 3*pooling_depth) in the order-0 sorted sequence, so
+    neither torch.unique nor a second sort is needed; one host sync for the (data dependent) cluster count."""
+
+    def __init__(self, in_channels, out_channels, stride=2, norm_layer=None, act_layer=None, reduce="max",
+                 shuffle_orders=True, traceable=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        assert stride == 2 ** (math.ceil(stride) - 1).bit_length()
+        self.stride = stride
+        assert reduce in ["sum", "mean", "min", "max"]
+        self.reduce, self.shuffle_orders, self.traceable = reduce, shuffle_orders, traceable
+        self.proj = nn.Linear(in_channels, out_channels)
+        if norm_layer is not None:
+            self.norm = PointSequential(norm_layer(out_channels))
+        if act_layer is not None:
+            self.act = PointSequential(act_layer())
+
+    def forward(self, point):
+        pooling_depth = (math.ceil(self.stride) - 1).bit_length()
+        if pooling_depth > point.serialized_depth:
+            pooling_depth = 0
+        assert {"serialized_code", "serialized_order", "serialized_inverse", "serialized_depth"}.issubset(point.keys())
+        n = point.feat.shape[0]
+        with torch.no_grad():
+            code = point.serialized_code >> pooling_depth * 3
+            # which row of the (possibly shuffled) code table is sorted by order row 0: all rows work the same way
+            order0 = point.serialized_order[0]
+            sc = code[0][order0]
+            flag = torch.ones_like(sc, dtype=torch.bool)
+            flag[1:] = sc[1:] != sc[:-1]
+            cid_sorted = torch.cumsum(flag, 0) - 1
+            cluster = torch.empty_like(cid_sorted)
+            cluster[order0] = cid_sorted
+            head_pos = torch.nonzero(flag).squeeze(1)                 # host sync: number of clusters
+            m = head_pos.shape[0]
+            head_indices = order0[head_pos]
+            lengths = torch.diff(head_pos, append=head_pos.new_full((1,), n))
+            code = code[:, head_indices]
+            key_bits = 3 * (point.serialized_depth - pooling_depth) + max(len(point.offset) - 1, 1).bit_length()
+            order, inverse = ops.serialize_sort(code, key_bits)
+            if self.shuffle_orders:
+                perm = torch.randperm(code.shape[0]).tolist()
+                code = torch.stack([code[i] for i in perm])
+                order = torch.stack([order[i] for i in perm])
+                inverse = torch.stack([inverse[i] for i in perm])
+            counts_host = None
+            if "offset_host" in point:
+                # scene sizes after pooling: count heads per scene (device) -> host together with nothing else to sync on
+                counts = torch.bincount(point.batch[head_indices], minlength=len(point.offset))
+                counts_host = counts.tolist()
+        feat_sorted = self.proj(point.feat)[order0]
+        feat = torch.segment_reduce(feat_sorted, self.reduce, lengths=lengths, axis=0, unsafe=True)
+        coord = torch.segment_reduce(point.coord[order0], "mean", lengths=lengths, axis=0, unsafe=True)
+        point_dict = dict(
+            feat=feat, coord=coord, grid_coord=point.grid_coord[head_indices] >> pooling_depth, serialized_code=code,
+            serialized_order=order, serialized_inverse=inverse, serialized_depth=point.serialized_depth - pooling_depth,
+            batch=point.batch[head_indices],
+        )
+        if counts_host is not None:
+            off, acc = [], 0
+            for c in counts_host:
+                acc += c
+                off.append(acc)
+            point_dict["offset_host"] = off
+            point_dict["offset"] = torch.tensor(off, device=feat.device, dtype=point.offset.dtype)
+        if "grid_max_host" in point:
+            point_dict["grid_max_host"] = [g >> pooling_depth for g in point["grid_max_host"]]
+        for k in ("condition", "context"):
+            if k in point:
+                point_dict[k] = point[k]
+        if self.traceable:
+            point_dict["pooling_inverse"] = cluster
+            point_dict["pooling_parent"] = point
+        point = Point(point_dict)
+        if getattr(self, "norm", None) is not None:
+            point = self.norm(point)
+        if getattr(self, "act", None) is not None:
+            point = self.act(point)
+        point.sparsify()
+        return point
+
+
+class SerializedUnpooling(PointModule):
+    """ptv3m1:447-482 (including the m1 quirk: parent.sparse_conv_feat is not refreshed after the add)."""
+
+    def __init__(self, in_channels, skip_channels, out_channels, norm_layer=None, act_layer=None, traceable=False):
+        super().__init__()
+        self.proj = PointSequential(nn.Linear(in_channels, out_channels))
+        self.proj_skip = PointSequential(nn.Linear(skip_channels, out_channels))
+        if norm_layer is not None:
+            self.proj.add(norm_layer(out_channels))
+            self.proj_skip.add(norm_layer(out_channels))
+        if act_layer is not None:
+            self.proj.add(act_layer())
+            self.proj_skip.add(act_layer())
+        self.traceable = traceable
+
+    def forward(self, point):
+        parent = point.pop("pooling_parent")
+        inverse = point.pop("pooling_inverse")
+        point = self.proj(point)
+        parent = self.proj_skip(parent)
+        parent.feat = parent.feat + point.feat[inverse]
+        if self.traceable:
+            parent["unpooling_parent"] = point
+        return parent
+
+
+class Embedding(PointModule):
+    def __init__(self, in_channels, embed_channels, norm_layer=None, act_layer=None):
+        super().__init__()
+        self.in_channels, self.embed_channels = in_channels, embed_channels
+        self.stem = PointSequential(conv=spconv.SubMConv3d(in_channels, embed_channels, kernel_size=5, padding=1, bias=False,
+                                                           indice_key="stem"))
+        if norm_layer is not None:
+            self.stem.add(norm_layer(embed_channels), name="norm")
+        if act_layer is not None:
+            self.stem.add(act_layer(), name="act")
+
+    def forward(self, point):
+        return self.stem(point)
+
+
+class PointTransformerV3(PointModule):
+    """ "PT-v3m1" (ptv3m1:518-714) with the same constructor arguments and defaults."""
+
+    def __init__(self, in_channels=6, order=("z", "z-trans"), stride=(2, 2, 2, 2), enc_depths=(2, 2, 2, 6, 2),
+                 enc_channels=(32, 64, 128, 256, 512), enc_num_head=(2, 4, 8, 16, 32), enc_patch_size=(48, 48, 48, 48, 48),
+                 dec_depths=(2, 2, 2, 2), dec_channels=(64, 64, 128, 256), dec_num_head=(4, 4, 8, 16),
+                 dec_patch_size=(48, 48, 48, 48), mlp_ratio=4, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0,
+                 drop_path=0.3, pre_norm=True, shuffle_orders=True, enable_rpe=False, enable_flash=True,
+                 upcast_attention=False, upcast_softmax=False, enc_mode=False, pdnorm_bn=False, pdnorm_ln=False,
+                 pdnorm_decouple=True, pdnorm_adaptive=False, pdnorm_affine=True,
+                 pdnorm_conditions=("ScanNet", "S3DIS", "Structured3D")):
+        super().__init__()
+        if pdnorm_bn or pdnorm_ln:
+            raise NotImplementedError("PDNorm (multi-dataset prompt training) is outside the PT-v3m1 hot path")
+        self.num_stages = len(enc_depths)
+        self.order = [order] if isinstance(order, str) else order
+        self.enc_mode, self.shuffle_orders = enc_mode, shuffle_orders
+        assert self.num_stages == len(stride) + 1 == len(enc_channels) == len(enc_num_head) == len(enc_patch_size)
+        assert enc_mode or self.num_stages == len(dec_depths) + 1 == len(dec_channels) + 1 == len(dec_num_head) + 1
+        bn_layer = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        ln_layer, act_layer = nn.LayerNorm, nn.GELU
+        self.embedding = Embedding(in_channels, enc_channels[0], norm_layer=bn_layer, act_layer=act_layer)
+
+        def make_block(ch, heads, patch, dp, i, s):
+            return Block(channels=ch, num_heads=heads, patch_size=patch, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                         qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=proj_drop, drop_path=dp, norm_layer=ln_layer,
+                         act_layer=act_layer, pre_norm=pre_norm, order_index=i % len(self.order), cpe_indice_key=f"stage{s}",
+                         enable_rpe=enable_rpe, enable_flash=enable_flash, upcast_attention=upcast_attention,
+                         upcast_softmax=upcast_softmax)
+
+        enc_dp = [x.item() for x in torch.linspace(0, drop_path, sum(enc_depths))]
+        self.enc = PointSequential()
+        for s in range(self.num_stages):
+            dps = enc_dp[sum(enc_depths[:s]): sum(enc_depths[: s + 1])]
+            enc = PointSequential()
+            if s > 0:
+                enc.add(SerializedPooling(enc_channels[s - 1], enc_channels[s], stride=stride[s - 1], norm_layer=bn_layer,
+                                          act_layer=act_layer), name="down")
+            for i in range(enc_depths[s]):
+                enc.add(make_block(enc_channels[s], enc_num_head[s], enc_patch_size[s], dps[i], i, s), name=f"block{i}")
+            if len(enc) != 0:
+                self.enc.add(module=enc, name=f"enc{s}")
+        if not enc_mode:
+            dec_dp = [x.item() for x in torch.linspace(0, drop_path, sum(dec_depths))]
+            self.dec = PointSequential()
+            dec_channels = list(dec_channels) + [enc_channels[-1]]
+            for s in reversed(range(self.num_stages - 1)):
+                dps = dec_dp[sum(dec_depths[:s]): sum(dec_depths[: s + 1])]
+                dps.reverse()
+                dec = PointSequential()
+                dec.add(SerializedUnpooling(dec_channels[s + 1], enc_channels[s], dec_channels[s], norm_layer=bn_layer,
+                                            act_layer=act_layer), name="up")
+                for i in range(dec_depths[s]):
+                    dec.add(make_block(dec_channels[s], dec_num_head[s], dec_patch_size[s], dps[i], i, s), name=f"block{i}")
+                self.dec.add(module=dec, name=f"dec{s}")
+
+    def forward(self, data_dict):
+        point = Point(data_dict)
+        point.serialization(order=self.order, shuffle_orders=self.shuffle_orders)
+        point.sparsify()
+        point = self.embedding(point)
+        point = self.enc(point)
+        if not self.enc_mode:
+            point = self.dec(point)
+        return point
+
+
+class PTv3Segmentor(nn.Module):
+    """backbone + linear head + cross-entropy: the part of DefaultSegmentorV2 (pointcept/models/default.py:41-95)
+    the fwd+bwd benchmark needs.  Parameter names match (``backbone.*``, ``seg_head.*``)."""
+
+    def __init__(self, num_classes=20, backbone_out_channels=64, **backbone_kwargs):
+        super().__init__()
+        self.backbone = PointTransformerV3(**backbone_kwargs)
+        self.seg_head = nn.Linear(backbone_out_channels, num_classes) if num_classes > 0 else nn.Identity()
+
+    def forward(self, input_dict):
+        point = self.backbone(input_dict)
+        seg_logits = self.seg_head(point.feat)
+        out = dict(seg_logits=seg_logits)
+        if "segment" in input_dict:
+            out["loss"] = nn.functional.cross_entropy(seg_logits.float(), input_dict["segment"], ignore_index=-1)
+        return out
+
+
+def ptv3_base_config():
+    """model kwargs of configs/scannet/semseg-pt-v3m1-0-base.py:11-47 ("PTv3-base")."""
+    return dict(
+        in_channels=6, order=("z", "z-trans", "hilbert", "hilbert-trans"), stride=(2, 2, 2, 2), enc_depths=(2, 2, 2, 6, 2),
+        enc_channels=(32, 64, 128, 256, 512), enc_num_head=(2, 4, 8, 16, 32), enc_patch_size=(1024,) * 5,
+        dec_depths=(2, 2, 2, 2), dec_channels=(64, 64, 128, 256), dec_num_head=(4, 4, 8, 16), dec_patch_size=(1024,) * 4,
+        mlp_ratio=4, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0, drop_path=0.3, shuffle_orders=True,
+        pre_norm=True, enable_rpe=False, enable_flash=True, upcast_attention=False, upcast_softmax=False, enc_mode=False,
+    )

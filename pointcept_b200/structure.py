@@ -1,0 +1,162 @@
+"""Host-side mirror of Pointcept's ``Point`` container (pointcept/models/utils/structure.py:20-148) and the
+``PointModule`` / ``PointSequential`` glue (pointcept/models/modules.py:28-111), re-designed so the
+serialization and sparsify steps run as fused device kernels without the reference's per-call host syncs:
+the scene sizes and grid extents are carried on the host next to the device tensors."""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .spconv import pytorch as spconv
+
+
+def offset2bincount(offset):
+    return torch.diff(offset, prepend=offset.new_zeros(1))
+
+
+def offset2batch(offset):
+    counts = offset2bincount(offset)
+    return torch.arange(len(counts), device=offset.device, dtype=torch.long).repeat_interleave(counts)
+
+
+def batch2offset(batch):
+    return torch.cumsum(batch.bincount(), dim=0).long()
+
+
+class Point(dict):
+    """dict with attribute access; same well-known keys as the reference (coord, grid_coord, feat, offset,
+    batch, serialized_*, sparse_shape, sparse_conv_feat, pooling_*).  Host-side companions:
+    ``offset_host`` (list[int]) and ``grid_max_host`` (list[int], per-axis max of grid_coord)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if "batch" not in self and "offset" in self:
+            if "offset_host" in self:  # no sync: sizes known on the host
+                oh = self["offset_host"]
+                counts = torch.tensor([b - a for a, b in zip([0] + list(oh[:-1]), oh)], device=self["offset"].device)
+                self["batch"] = torch.repeat_interleave(torch.arange(len(oh), device=counts.device), counts,
+                                                        output_size=int(oh[-1]))
+            else:
+                self["batch"] = offset2batch(self["offset"])
+        elif "offset" not in self and "batch" in self:
+            self["offset"] = batch2offset(self["batch"])
+
+    # -- host companions (one D2H each, only if the caller did not provide them) ---------------------
+    def host_offset(self):
+        if "offset_host" not in self:
+            self["offset_host"] = [int(v) for v in self["offset"].tolist()]
+        return self["offset_host"]
+
+    def host_grid_max(self):
+        if "grid_max_host" not in self:
+            self["grid_max_host"] = [int(v) for v in self["grid_coord"].max(0).values.tolist()]
+        return self["grid_max_host"]
+
+    def _ensure_grid(self):
+        if "grid_coord" not in self:
+            assert {"grid_size", "coord"}.issubset(self.keys())
+            self["grid_coord"] = torch.div(self.coord - self.coord.min(0)[0], self.grid_size, rounding_mode="trunc").int()
+
+    def serialization(self, order="z", depth=None, shuffle_orders=False):
+        """structure.py:53-110: codes for every order, argsort and inverse -- two fused kernels + radix sort."""
+        order = [order] if isinstance(order, str) else list(order)
+        self["order"] = order
+        assert "batch" in self
+        self._ensure_grid()
+        if depth is None:
+            depth = int(max(self.host_grid_max()) + 1).bit_length()
+        self["serialized_depth"] = depth
+        n_scene = len(self["offset"])
+        assert depth * 3 + n_scene.bit_length() <= 63
+        assert depth <= 16
+        code = ops.serialize_encode(self["grid_coord"], self["batch"], depth, order)
+        key_bits = 3 * depth + max(n_scene - 1, 1).bit_length()
+        sorder, inverse = ops.serialize_sort(code, key_bits)
+        if shuffle_orders:
+            perm = torch.randperm(len(order)).tolist()
+            code = torch.stack([code[i] for i in perm])
+            sorder = torch.stack([sorder[i] for i in perm])
+            inverse = torch.stack([inverse[i] for i in perm])
+        self["serialized_code"] = code
+        self["serialized_order"] = sorder
+        self["serialized_inverse"] = inverse
+
+    def sparsify(self, pad=96):
+        """structure.py:112-148: wrap feat / (batch, grid_coord) into a SparseConvTensor."""
+        assert {"feat", "batch"}.issubset(self.keys())
+        self._ensure_grid()
+        if "sparse_shape" in self:
+            sparse_shape = self["sparse_shape"]
+        else:
+            sparse_shape = [m + pad for m in self.host_grid_max()]
+        indices = torch.cat([self["batch"].unsqueeze(-1).int(), self["grid_coord"].int()], dim=1).contiguous()
+        self["sparse_shape"] = sparse_shape
+        self["sparse_conv_feat"] = spconv.SparseConvTensor(features=self["feat"], indices=indices, spatial_shape=sparse_shape,
+                                                           batch_size=len(self["offset"]))
+
+
+class PointModule(nn.Module):
+    """Modules that take and return a Point (modules.py:28-34)."""
+
+
+class PointSequential(PointModule):
+    """modules.py:37-111: dispatch on module kind; child naming identical to the reference (checkpoint ABI)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        if len(args) == 1 and isinstance(args[0], OrderedDict):
+            for key, module in args[0].items():
+                self.add_module(key, module)
+        else:
+            for idx, module in enumerate(args):
+                self.add_module(str(idx), module)
+        for name, module in kwargs.items():
+            if name in self._modules:
+                raise ValueError("name exists.")
+            self.add_module(name, module)
+
+    def __getitem__(self, idx):
+        if not (-len(self) <= idx < len(self)):
+            raise IndexError("index {} is out of range".format(idx))
+        return list(self._modules.values())[idx % len(self)]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def add(self, module, name=None):
+        if name is None:
+            name = str(len(self._modules))
+            if name in self._modules:
+                raise KeyError("name exists")
+        self.add_module(name, module)
+
+    def forward(self, input):
+        for module in self._modules.values():
+            if isinstance(module, PointModule):
+                input = module(input)
+            elif spconv.modules.is_spconv_module(module):
+                if isinstance(input, Point):
+                    input.sparse_conv_feat = module(input.sparse_conv_feat)
+                    input.feat = input.sparse_conv_feat.features
+                else:
+                    input = module(input)
+            elif isinstance(input, Point):
+                input.feat = module(input.feat)
+                if "sparse_conv_feat" in input:
+                    input.sparse_conv_feat = input.sparse_conv_feat.replace_feature(input.feat)
+            elif isinstance(input, spconv.SparseConvTensor):
+                if input.indices.shape[0] != 0:
+                    input = input.replace_feature(module(input.features))
+            else:
+                input = module(input)
+        return input

@@ -135,8 +135,51 @@ def gen_point_and_padding():
     print("attention_dense.npz")
 
 
+from oracle.ptv3_cpu import TINY_CFG  # noqa: E402
+
+
+def gen_ptv3_tiny():
+    """The UNMODIFIED reference PT-v3m1 (non-flash fp32 attention branch) run on CPU, with spconv stood in by
+    oracle/spconv_ref.py.  Pins the model-level restatement (blocks, pooling, unpooling quirk, padding)."""
+    ref = ref_import.load_models(use_shims="oracle")
+    from pointcept_b200 import synth
+    torch.manual_seed(3)
+    cfg = dict(TINY_CFG, enable_flash=False, upcast_attention=True, upcast_softmax=True)
+    model = ref.ptv3.PointTransformerV3(**cfg)
+    model.train()
+    # SerializedPooling is built with its own default shuffle_orders=True (ptv3m1:607-617 never forwards the
+    # model-level flag), i.e. the reference is random by design below stage 0: pin it for the fixture.
+    for m in model.modules():
+        if hasattr(m, "shuffle_orders"):
+            m.shuffle_orders = False
+    scenes = [synth.indoor_scene(11, target_voxels=1400), synth.indoor_scene(12, target_voxels=1000)]
+    grid = np.concatenate([s[1] for s in scenes])
+    coord = np.concatenate([s[0] for s in scenes])
+    offset = np.cumsum([len(s[1]) for s in scenes])
+    feat = torch.randn(len(grid), 6)
+    out = model(dict(coord=torch.from_numpy(coord), grid_coord=torch.from_numpy(grid), feat=feat,
+                     offset=torch.from_numpy(offset)))
+    g = torch.randn_like(out.feat)
+    out.feat.backward(g)
+    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    keep = ("embedding.stem.conv.weight", "enc.enc0.block0.cpe.0.weight", "enc.enc0.block1.attn.qkv.weight",
+            "enc.enc1.down.proj.weight", "enc.enc2.block1.cpe.0.weight", "dec.dec0.block0.cpe.0.weight",
+            "dec.dec0.up.proj_skip.0.weight", "dec.dec1.block1.attn.proj.weight")
+    grads = {"grad::" + k: p.grad.numpy() for k, p in model.named_parameters() if k in keep}
+    np.savez_compressed(os.path.join(OUT, "ptv3_tiny.npz"), coord=coord, grid_coord=grid, offset=offset, feat=feat.numpy(),
+                        out=out.feat.detach().numpy(), dout=g.numpy(), **{"sd::" + k: v for k, v in sd.items()}, **grads)
+    print("ptv3_tiny.npz", out.feat.shape, float(out.feat.abs().mean()))
+
+
+if __name__ == "__main__" and "--only-tiny" in sys.argv:
+    gen_ptv3_tiny()
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
-    gen_serialization()
-    gen_point_and_padding()
+    if "--only-tiny" not in sys.argv:
+        gen_serialization()
+        gen_point_and_padding()
+        gen_ptv3_tiny()
+

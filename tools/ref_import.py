@@ -56,6 +56,53 @@ def load_serialization():
     return _load(pkg + ".default", "pointcept/models/utils/serialization/default.py")
 
 
+def _install_oracle_spconv():
+    """CPU stand-in for spconv built on oracle/spconv_ref.py, so the UNMODIFIED reference model files run
+    on CPU (fixture generation / pinning the model-level restatement; spconv arithmetic itself stays unpinned)."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    from oracle import spconv_ref as osp
+
+    class SparseConvTensor:
+        def __init__(self, features, indices, spatial_shape, batch_size, indice_dict=None, **kw):
+            self.features, self.indices = features, indices
+            self.spatial_shape, self.batch_size = list(spatial_shape), batch_size
+            self.indice_dict = indice_dict if indice_dict is not None else {}
+
+        def replace_feature(self, f):
+            return SparseConvTensor(f, self.indices, self.spatial_shape, self.batch_size, self.indice_dict)
+
+    class SparseModule(nn.Module):
+        pass
+
+    class SubMConv3d(SparseModule):
+        def __init__(self, cin, cout, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True, indice_key=None, **kw):
+            super().__init__()
+            self.k, self.indice_key = kernel_size, indice_key
+            self.weight = nn.Parameter(torch.empty(cout, kernel_size, kernel_size, kernel_size, cin))
+            self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+            nn.init.normal_(self.weight, std=0.05)
+
+        def forward(self, x):
+            key = (self.indice_key, self.k)
+            if self.indice_key is None or key not in x.indice_dict:
+                pair = osp.subm_rulebook(x.indices.numpy(), x.spatial_shape, self.k)
+                if self.indice_key is not None:
+                    x.indice_dict[key] = pair
+            else:
+                pair = x.indice_dict[key]
+            w = self.weight.reshape(self.weight.shape[0], -1, self.weight.shape[-1])
+            return x.replace_feature(osp.conv_apply(x.features, w, pair, self.bias))
+
+    sp = _mod("spconv")
+    spt = _mod("spconv.pytorch", SubMConv3d=SubMConv3d, SparseConv3d=None, SparseInverseConv3d=None,
+               SparseModule=SparseModule, SparseSequential=nn.Sequential, Identity=nn.Identity,
+               SparseConvTensor=SparseConvTensor)
+    spt.modules = _mod("spconv.pytorch.modules", is_spconv_module=lambda m: isinstance(m, SparseModule))
+    sp.pytorch = spt
+
+
 def load_models(use_shims=False):
     """Import structure.py, modules.py, PT-v3m1 and SpUNet-v1m1 from the reference.
 
@@ -90,7 +137,10 @@ def load_models(use_shims=False):
     _mod("torch_geometric")
     _mod("torch_geometric.utils", scatter=None)
 
-    if use_shims:
+    if use_shims == "oracle":
+        _install_oracle_spconv()
+        sys.modules["flash_attn"] = None
+    elif use_shims:
         import pointcept_b200
         pointcept_b200.install(flash_attn=True)
     else:

@@ -44,6 +44,8 @@ enum { B2PC_ORDER_Z = 0, B2PC_ORDER_Z_TRANS = 1, B2PC_ORDER_HILBERT = 2, B2PC_OR
 
 int b2pc_version(void);
 const char* b2pc_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long b2pc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Serialization: replaces encode() (serialization/default.py:9-24, z_order.py:66-101,
@@ -108,10 +110,10 @@ int b2pc_rulebook_subm(const int32_t* indices, int64_t n, const int* spatial_sha
                        void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
 /* Strided (SparseConv3d): out coordinate o is active iff some input i and offset k satisfy
  * i = o*stride - padding + k*dilation.  Output rows are the distinct out coordinates in
- * ascending (b,x,y,z) order.  out_indices [cap,4], pair_fwd [KV,cap] (row stride = cap),
- * pair_bwd [KV,N]; *num_out (device int64) receives M <= cap.  Stage 1 of 2: counts the
- * distinct outputs; the caller reads *num_out (one host sync, as spconv does) and calls
- * b2pc_rulebook_strided_finish with it. */
+ * ascending (b,x,y,z) order.  Two stages because M is data dependent: _begin counts the distinct
+ * outputs into *num_out (device int64); the caller reads it (one host sync, as spconv does),
+ * allocates out_indices [M,4], pair_fwd [KV,M], pair_bwd [KV,N] and calls _finish with the SAME
+ * workspace (its contents carry over). */
 int b2pc_rulebook_strided_begin(const int32_t* indices, int64_t n, const int* spatial_shape_host,
                                 const int* ksize_host, const int* stride_host, const int* padding_host,
                                 const int* dilation_host, int64_t* num_out, void* workspace,

@@ -17,6 +17,7 @@ c_i32p = ctypes.c_void_p
 _SIGS = {
     "b2pc_version": (ctypes.c_int, []),
     "b2pc_last_error": (ctypes.c_char_p, []),
+    "b2pc_launch_count": (ctypes.c_longlong, []),
     "b2pc_serialize_encode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                              ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "b2pc_serialize_sort_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
@@ -55,7 +56,10 @@ EXPORTS = tuple(_SIGS)
 
 def build(verbose=False, extra_flags=()):
     """Compile libb2pc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + [os.path.join(CSRC, "b2pc.cu"), "-o", LIB_PATH]
+    extra_flags = list(extra_flags)
+    if not os.path.exists(os.path.join(CSRC, "attn_umma.cuh")) and "-DB2PC_NO_UMMA" not in extra_flags:
+        extra_flags.append("-DB2PC_NO_UMMA")
+    cmd = ["nvcc"] + NVCC_FLAGS + extra_flags + [os.path.join(CSRC, "b2pc.cu"), "-o", LIB_PATH]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)

@@ -217,6 +217,7 @@ inline int launch_attn_fwd_simt(const void* qkv, const int32_t* cu, int n_seq, i
     default: set_error("patch_attn_fwd(simt): head_dim %d not in {16,32,64}", D); return B2PC_ERR_UNSUPPORTED;
   }
 #undef B2PC_AF
+  count_launches(1);
   B2PC_CHECK_LAUNCH("patch_attn_fwd(simt)");
   return B2PC_OK;
 }
@@ -244,6 +245,7 @@ inline int launch_attn_bwd_simt(const void* dout, const void* qkv, const void* o
     default: set_error("patch_attn_bwd(simt): head_dim %d not in {16,32,64}", D); return B2PC_ERR_UNSUPPORTED;
   }
 #undef B2PC_AB
+  count_launches(3);
   B2PC_CHECK_LAUNCH("patch_attn_bwd(simt)");
   return B2PC_OK;
 }

@@ -12,7 +12,11 @@
 #include "attn_umma.cuh"
 #endif
 
+#include <atomic>
+
 namespace b2pc {
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -28,6 +32,7 @@ extern "C" {
 
 int b2pc_version(void) { return 100; }
 const char* b2pc_last_error(void) { return g_err; }
+long long b2pc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int b2pc_serialize_encode(const int32_t* grid_coord, const int64_t* batch, int64_t n, int depth, const int* orders_host,
                           int n_orders, int64_t* code, b2pc_stream_t stream) {

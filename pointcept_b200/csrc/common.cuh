@@ -13,6 +13,7 @@ namespace b2pc {
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);  // kernels launched by this library (b2pc_launch_count)
 
 #define B2PC_CHECK_ARG(cond, ...)                 \
   do {                                            \

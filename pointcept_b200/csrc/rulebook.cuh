@@ -230,6 +230,7 @@ inline int launch_rulebook_subm(const int32_t* indices, int64_t n, const int* sh
   fill_i32_kernel<<<grid_for(r.slots), 256, 0, stream>>>(r.vals, r.slots, 0x7FFFFFFF);
   hash_insert_rows_kernel<<<grid_for(n), 256, 0, stream>>>((const int4*)indices, n, g, r.keys, r.vals, mask);
   subm_pairs_kernel<<<grid_for(n), 256, 0, stream>>>((const int4*)indices, n, g, r.keys, r.vals, mask, pair);
+  count_launches(4);
   B2PC_CHECK_LAUNCH("rulebook_subm");
   return B2PC_OK;
 }
@@ -248,6 +249,7 @@ inline int launch_rulebook_strided_begin(const int32_t* indices, int64_t n, cons
   hash_clear_kernel<<<grid_for(r.slots), 256, 0, stream>>>(r.keys, r.slots);
   strided_collect_kernel<<<grid_for(n), 256, 0, stream>>>((const int4*)indices, n, g, r.keys, (uint32_t)(r.slots - 1), r.uniq,
                                                           (unsigned long long*)num_out);
+  count_launches(2);
   B2PC_CHECK_LAUNCH("rulebook_strided_begin");
   return B2PC_OK;
 }
@@ -265,21 +267,18 @@ inline int launch_rulebook_strided_finish(const int32_t* indices, int64_t n, con
   RulebookWs r = carve_rulebook_ws(ws, n, g.kv);
   const uint32_t mask = (uint32_t)(r.slots - 1);
   // ascending linearised (b,x,y,z): sort the distinct keys on their significant bits
-  uint64_t maxkey = (uint64_t)0x7FFFFFFF;  // batch < 2^31 is never reached; bound via shapes below
+  // key < batch * prod(oshape); the batch count is not part of the geometry, allow up to 2^20 scenes
+  int key_bits = 0;
   {
-    // key < B * prod(oshape); B unknown here -> use 63 bits minus leading zeros of prod(oshape)*2^20
-    unsigned __int128 prod = (unsigned __int128)g.oshape[0] * g.oshape[1] * g.oshape[2];
-    prod <<= 20;  // up to 2^20 scenes per batch
-    int bits = 0;
-    while (bits < 64 && (prod >> bits) != 0) ++bits;
-    maxkey = bits;
+    unsigned __int128 bound = ((unsigned __int128)g.oshape[0] * g.oshape[1] * g.oshape[2]) << 20;
+    while (key_bits < 64 && (bound >> key_bits) != 0) ++key_bits;
   }
-  const int key_bits = (int)(maxkey > 64 ? 64 : maxkey);
   rc = launch_sort((const int64_t*)r.uniq, m, 1, key_bits, r.order, r.inverse, r.sort_ws, r.sort_bytes, stream);
   if (rc) return rc;
   strided_assign_kernel<<<grid_for(m), 256, 0, stream>>>(r.order, r.uniq, m, g, r.keys, r.vals, mask, out_indices);
   fill_i32_kernel<<<grid_for(m * g.kv), 256, 0, stream>>>(pair_fwd, m * (int64_t)g.kv, -1);
   strided_pairs_kernel<<<grid_for(n), 256, 0, stream>>>((const int4*)indices, n, m, g, r.keys, r.vals, mask, pair_fwd, pair_bwd);
+  count_launches(3);
   B2PC_CHECK_LAUNCH("rulebook_strided_finish");
   return B2PC_OK;
 }

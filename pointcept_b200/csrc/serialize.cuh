@@ -84,6 +84,7 @@ inline int launch_encode(const int32_t* grid, const int64_t* batch, int64_t n, i
   int blocks = (int)ceil_div(n, 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   encode_kernel<<<blocks, 256, 0, stream>>>(grid, batch, n, depth, eo, code);
+  count_launches(1);
   B2PC_CHECK_LAUNCH("serialize_encode");
   return B2PC_OK;
 }
@@ -119,7 +120,6 @@ padding_kernel(const int64_t* __restrict__ offset, int B, int K, int64_t n, int6
       if (local >= cntp - K + r) local -= K;  // borrowed tail: copy of the slot K earlier
     }
     pad[t] = o[b] + local;
-    if (local == t - op[b] && (t - op[b]) % K == 0) {}  // (no-op; cu handled below)
   }
   for (int64_t i = gid; i < n; i += stride) {
     int lo = 0, hi = B;
@@ -150,6 +150,7 @@ inline int launch_padding(const int64_t* offset, int B, int K, int64_t n, int64_
   int blocks = (int)ceil_div(work > 0 ? work : 1, 256);
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
   padding_kernel<<<blocks, 256, (2 * B + 2) * sizeof(int64_t), stream>>>(offset, B, K, n, t_pad, n_seq, pad, unpad, cu);
+  count_launches(1);
   B2PC_CHECK_LAUNCH("patch_padding");
   return B2PC_OK;
 }

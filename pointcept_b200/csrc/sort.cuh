@@ -187,6 +187,7 @@ inline int launch_sort(const int64_t* code, int64_t n, int n_orders, int key_bit
       sort_scatter_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(kin, vin, kout, vout, order, inverse, n, shift, nblocks, counts);
     kin = kout;
     vin = vout;
+    count_launches(3);
   }
   B2PC_CHECK_LAUNCH("serialize_sort");
   return B2PC_OK;

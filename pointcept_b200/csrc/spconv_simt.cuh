@@ -86,6 +86,7 @@ inline int launch_gather_gemm_simt(const void* feat, const void* weight, const v
   dim3 grid((unsigned)ceil_div(n_out, kCgTileM), (unsigned)ceil_div(c_out, kCgTileN));
   gather_gemm_simt_kernel<T><<<grid, 256, 0, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride,
                                                        n_out, c_in, c_out, kv, transpose_w, flip, (T*)out);
+  count_launches(1);
   B2PC_CHECK_LAUNCH("spconv_gather_gemm(simt)");
   return B2PC_OK;
 }
@@ -190,6 +191,7 @@ inline int launch_bwd_weight_simt(const void* feat, const void* dout, const int3
                                                       kv, splits, (float*)ws);
   int rb = (int)ceil_div(elems, 256); if (rb > kNumSMs * 8) rb = kNumSMs * 8;
   reduce_splits_kernel<<<rb, 256, 0, stream>>>((const float*)ws, elems, splits, dweight);
+  count_launches(2);
   B2PC_CHECK_LAUNCH("spconv_bwd_weight(simt)");
   return B2PC_OK;
 }

@@ -25,6 +25,37 @@ def get_impl():
     return _impl
 
 
+# optional per-op CUDA-event timing (bench.py's roofline leg): name -> list of (start, end, meta)
+_prof = None
+
+
+def profile_start():
+    global _prof
+    _prof = {}
+
+
+def profile_stop():
+    global _prof
+    p, _prof = _prof, None
+    return p
+
+
+class _timed:
+    def __init__(self, name, meta):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            self.e1.record()
+            _prof.setdefault(self.name, []).append((self.e0, self.e1, self.meta))
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -122,8 +153,9 @@ class PatchAttentionFn(torch.autograd.Function):
         out = torch.empty((T, H, D), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((H, T), dtype=torch.float32, device=qkv.device)
         L = _lib.lib()
-        _lib.check(L.b2pc_patch_attn_fwd(_p(qkv), _DTYPES[qkv.dtype], _p(cu), cu.numel() - 1, int(max_seqlen), T, H, D,
-                                         float(scale), _p(out), _p(lse), _impl, _stream()), "patch_attn_fwd")
+        with _timed("patch_attn_fwd", (cu, H, D)):
+            _lib.check(L.b2pc_patch_attn_fwd(_p(qkv), _DTYPES[qkv.dtype], _p(cu), cu.numel() - 1, int(max_seqlen), T, H, D,
+                                             float(scale), _p(out), _p(lse), _impl, _stream()), "patch_attn_fwd")
         ctx.save_for_backward(qkv, out, lse, cu)
         ctx.max_seqlen, ctx.scale = int(max_seqlen), float(scale)
         ctx.mark_non_differentiable(lse)
@@ -137,9 +169,10 @@ class PatchAttentionFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         L = _lib.lib()
         ws = _ws(L.b2pc_patch_attn_bwd_workspace_bytes(T, H, D), qkv.device)
-        _lib.check(L.b2pc_patch_attn_bwd(_p(dout), _p(qkv), _p(out), _p(lse), _DTYPES[qkv.dtype], _p(cu), cu.numel() - 1,
-                                         ctx.max_seqlen, T, H, D, ctx.scale, _p(dqkv), _p(ws), ws.numel(), _impl, _stream()),
-                   "patch_attn_bwd")
+        with _timed("patch_attn_bwd", (cu, H, D)):
+            _lib.check(L.b2pc_patch_attn_bwd(_p(dout), _p(qkv), _p(out), _p(lse), _DTYPES[qkv.dtype], _p(cu), cu.numel() - 1,
+                                             ctx.max_seqlen, T, H, D, ctx.scale, _p(dqkv), _p(ws), ws.numel(), _impl, _stream()),
+                       "patch_attn_bwd")
         return dqkv, None, None, None
 
 
@@ -207,9 +240,10 @@ def rulebook_strided(indices, spatial_shape, ksize, stride, padding=0, dilation=
 def _gather_gemm(feat, weight, bias, pair, n_out, c_in, c_out, kv, transpose_w, flip):
     out = torch.empty((n_out, c_out), dtype=feat.dtype, device=feat.device)
     L = _lib.lib()
-    _lib.check(L.b2pc_spconv_gather_gemm(_p(feat), _p(weight), _p(bias), _p(pair), pair.shape[1], feat.shape[0], n_out, c_in, c_out,
-                                         kv, int(transpose_w), int(flip), _DTYPES[feat.dtype], _p(out), _impl, _stream()),
-               "spconv_gather_gemm")
+    with _timed("spconv_gather_gemm", (pair, c_in, c_out, feat.element_size())):
+        _lib.check(L.b2pc_spconv_gather_gemm(_p(feat), _p(weight), _p(bias), _p(pair), pair.shape[1], feat.shape[0], n_out, c_in,
+                                             c_out, kv, int(transpose_w), int(flip), _DTYPES[feat.dtype], _p(out), _impl, _stream()),
+                   "spconv_gather_gemm")
     return out
 
 
@@ -253,9 +287,10 @@ class SparseConvFn(torch.autograd.Function):
             L = _lib.lib()
             n_out = table_fwd.shape[1]
             ws = _ws(L.b2pc_spconv_bwd_weight_workspace_bytes(n_out, c_in, c_out, kv), feat.device)
-            _lib.check(L.b2pc_spconv_bwd_weight(_p(feat), _p(dout), _p(table_fwd), table_fwd.shape[1], feat.shape[0], n_out, c_in,
-                                                c_out, kv, _DTYPES[feat.dtype], _p(dweight), _p(ws), ws.numel(), _impl, _stream()),
-                       "spconv_bwd_weight")
+            with _timed("spconv_bwd_weight", (table_fwd, c_in, c_out, feat.element_size())):
+                _lib.check(L.b2pc_spconv_bwd_weight(_p(feat), _p(dout), _p(table_fwd), table_fwd.shape[1], feat.shape[0], n_out, c_in,
+                                                    c_out, kv, _DTYPES[feat.dtype], _p(dweight), _p(ws), ws.numel(), _impl, _stream()),
+                           "spconv_bwd_weight")
             if ctx.wdtype != torch.float32:
                 dweight = dweight.to(ctx.wdtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:

@@ -1,0 +1,107 @@
+"""Host-side logic that needs no GPU: synthetic scenes, the reference-compatible module tree, the drop-in
+import surface, and the N>1 sharding / reduction logic of bench.py under gloo (world_size 2)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from pointcept_b200 import synth
+from tools import ref_import
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synthetic_scene_is_seeded_and_calibrated():
+    c1, g1 = synth.indoor_scene(3, target_voxels=20_000)
+    c2, g2 = synth.indoor_scene(3, target_voxels=20_000)
+    assert np.array_equal(g1, g2) and len(g1) == 20_000
+    assert len(np.unique(g1, axis=0)) == len(g1)          # voxels are unique
+    assert g1.min() == 0
+    nb = synth.neighbour_stats(g1)
+    assert 8.0 < nb < 14.0, nb                              # ~11 active 3^3 neighbours
+    b = synth.make_batch(3, seed=1, target_voxels=5000)
+    assert b["offset"].tolist() == [5000, 10000, 15000] and b["feat"].shape == (15000, 6)
+
+
+def test_dropin_modules_register_under_reference_import_names():
+    import pointcept_b200
+    pointcept_b200.install(flash_attn=True)
+    import flash_attn
+    import spconv.pytorch as spconv
+    assert spconv.modules.is_spconv_module(spconv.SubMConv3d(4, 8, 3))
+    assert not spconv.modules.is_spconv_module(torch.nn.Linear(2, 2))
+    m = spconv.SparseConv3d(4, 8, kernel_size=2, stride=2, bias=False, indice_key="spconv1")
+    assert tuple(m.weight.shape) == (8, 2, 2, 2, 4) and m.bias is None
+    assert tuple(spconv.SubMConv3d(6, 32, kernel_size=5, padding=1, bias=False, indice_key="stem").weight.shape) == (32, 5, 5, 5, 6)
+    assert callable(flash_attn.flash_attn_varlen_qkvpacked_func)
+    x = spconv.SparseConvTensor(torch.zeros(3, 4), torch.zeros(3, 4, dtype=torch.int32), [8, 8, 8], 1)
+    y = x.replace_feature(torch.ones(3, 2))
+    assert y.indice_dict is x.indice_dict and y.features.shape == (3, 2)
+    with pytest.raises(NotImplementedError):
+        flash_attn.flash_attn_varlen_qkvpacked_func(torch.zeros(4, 3, 1, 16), torch.tensor([0, 4]), 4, dropout_p=0.1)
+    for k in [k for k in sys.modules if k == "spconv" or k.startswith("spconv.") or k.startswith("flash_attn")]:
+        del sys.modules[k]
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference only exists in the authoring container")
+def test_unmodified_reference_models_build_on_the_dropins_with_identical_state_dict():
+    """The reference's own PT-v3m1 / SpUNet-v1m1 files, imported unmodified on top of our spconv / flash_attn
+    modules, produce the same parameter names and shapes as the mirrors (checkpoint ABI)."""
+    from pointcept_b200.ptv3 import PointTransformerV3, ptv3_base_config
+    from pointcept_b200.spunet import SpUNetBase
+    ref = ref_import.load_models(use_shims=True)
+    a = {k: tuple(v.shape) for k, v in PointTransformerV3(**ptv3_base_config()).state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.ptv3.PointTransformerV3(**ptv3_base_config()).state_dict().items()}
+    assert a == b and len(a) > 400
+    a = {k: tuple(v.shape) for k, v in SpUNetBase(6, 20).state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.spunet.SpUNetBase(6, 20).state_dict().items()}
+    assert a == b and len(a) > 300
+    for k in [k for k in sys.modules if k.split(".")[0] in ("spconv", "flash_attn", "pointcept", "addict", "timm", "torch_scatter", "torch_geometric")]:
+        del sys.modules[k]
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the reductions bench.py performs: total points (SUM) and step time (MAX over ranks)
+    hb = synth.make_batch(2, seed=100 + rank, target_voxels=1500 + 100 * rank)
+    pts = torch.tensor([float(hb["offset"][-1])], dtype=torch.float64)
+    dist.all_reduce(pts, op=dist.ReduceOp.SUM)
+    ms = torch.tensor([10.0 + 5 * rank], dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # DDP gradient averaging on a parameter set shaped like ours (plain nn.Parameters, all used every step)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(8, 4)
+    ddp = torch.nn.parallel.DistributedDataParallel(lin, broadcast_buffers=False)
+    x = torch.full((3, 8), float(rank + 1))
+    ddp(x).sum().backward()
+    if rank == 0:
+        json.dump(dict(points=pts.item(), ms=ms.item(), grad=lin.weight.grad[0, 0].item()), open(out, "w"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_reductions(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r.json")
+    mp.spawn(_gloo_worker, args=(2, 29611, out), nprocs=2, join=True)
+    r = json.load(open(out))
+    assert r["points"] == 2 * 1500 + 2 * 1600       # different scenes per rank, whole scenes only
+    assert r["ms"] == 15.0                           # max over ranks
+    assert abs(r["grad"] - 3 * (1 + 2) / 2) < 1e-6   # DDP averages gradients
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-voxels", "2500"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "points/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0

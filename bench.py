@@ -38,8 +38,35 @@ def parse():
     ap.add_argument("--voxels", type=int, default=120_000, help="voxels per synthetic scene")
     ap.add_argument("--cpu-voxels", type=int, default=120_000, help="scene size of the bounded CPU sample (one scene)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-timeout", type=int, default=240)
     ap.add_argument("--kernel-impl", type=int, default=None, help="0 auto, 1 SIMT kernels, 2 tcgen05 kernels")
     return ap.parse_args()
+
+
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def host_cores():
+    """usable host cores: affinity mask, further limited by a cgroup cpu quota if one is set"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return max(1, n)
 
 
 def peaks():
@@ -109,7 +136,7 @@ def cpu_step_fn(voxels, seed=0):
     from pointcept_b200 import synth
     from pointcept_b200.ptv3 import PTv3Segmentor, ptv3_base_config
 
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     cfg = ptv3_base_config()
     torch.manual_seed(0)
@@ -137,9 +164,12 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     step, n, cores = cpu_step_fn(args.cpu_voxels)
-    for _ in range(max(1, min(args.warmup, 1))):
-        step()
-    steps = max(1, min(args.steps, 2))
+    log(f"reference arm: {n} voxels on {cores} host cores")
+    t0 = time.perf_counter()
+    step()                                   # warm-up (also tells us how long a step takes)
+    warm = time.perf_counter() - t0
+    log(f"warm-up step {warm:.1f}s")
+    steps = max(1, min(args.steps, 3, int(90.0 / max(warm, 1e-3))))   # keep the whole arm within a few minutes
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
@@ -212,9 +242,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     resident = to_device()
-    for _ in range(max(args.warmup, 3)):
+    log(f"rank {rank}: model on device, {n_points} points per step; warm-up")
+    for i in range(max(args.warmup, 3)):
         step(resident)
+        if i == 0:
+            torch.cuda.synchronize()
+            log("first step done")
     sync_all()
+    log("warm-up done; timed region 1")
 
     # ---- timed region 1: inputs resident in HBM, CUDA events, max over ranks ------------------------------
     launches0 = _lib.lib().b2pc_launch_count()
@@ -241,6 +276,7 @@ def run_ours(args):
     total_points = float(pts.item())
     value = total_points * args.steps / (ms_total * 1e-3)
 
+    log(f"timed region 1: {ms_total / args.steps:.1f} ms/step; timed region 2 (e2e)")
     # ---- timed region 2: end to end through the public API with HOST buffers ---------------------------------
     sync_all()
     t0 = time.perf_counter()
@@ -291,13 +327,16 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cstep, cn, cores = cpu_step_fn(args.cpu_voxels)
-        cstep()
-        t0 = time.perf_counter()
-        cstep()
-        cdt = time.perf_counter() - t0
-        cpu = dict(value=cn / cdt, unit=UNIT, cores=cores, kind="port",
-                   sample=f"1 scene x {cn} voxels, PTv3-base fwd+bwd fp32 (oracle/ptv3_cpu.py, torch CPU), 1 warm-up + 1 timed step")
+        log("cpu_baseline: running the oracle port on the host cores (bounded subprocess)")
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                                "--cpu-voxels", str(args.cpu_voxels)], capture_output=True, text=True, timeout=args.cpu_timeout,
+                               env=dict(os.environ, RANK="0", WORLD_SIZE="1", CUDA_VISIBLE_DEVICES=""))
+            js = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+            cpu = json.loads(js[-1])["cpu_baseline"] if js else dict(value=None, unit=UNIT, error=p.stderr[-300:])
+        except subprocess.TimeoutExpired:
+            cpu = dict(value=None, unit=UNIT, cores=host_cores(), kind="port",
+                       sample=f"1 scene x {args.cpu_voxels} voxels", error=f"did not finish within {args.cpu_timeout}s")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -94,6 +94,8 @@ def serialize_encode(grid_coord, batch, depth, orders):
     n = gc.shape[0]
     ids = (ctypes.c_int * len(orders))(*[ORDER_IDS[o] for o in orders])
     code = torch.empty((len(orders), n), dtype=torch.int64, device=gc.device)
+    if n == 0:
+        return code
     L = _lib.lib()
     _lib.check(L.b2pc_serialize_encode(_p(gc), _p(batch), n, int(depth), ids, len(orders), _p(code), _stream()), "serialize_encode")
     return code
@@ -107,6 +109,8 @@ def serialize_sort(code, key_bits):
     k, n = code.shape
     order = torch.empty_like(code)
     inverse = torch.empty_like(code)
+    if n == 0:
+        return order, inverse
     L = _lib.lib()
     ws = _ws(L.b2pc_serialize_sort_workspace_bytes(n, k), code.device)
     _lib.check(L.b2pc_serialize_sort(_p(code), n, k, int(key_bits), _p(order), _p(inverse), _p(ws), ws.numel(), _stream()),

@@ -245,11 +245,13 @@ def _attn_case(lens, H, D, dtype, impl, seed=0, tol_out=2e-3, tol_grad=4e-3):
                                     ([2048, 100], 1)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_patch_attention_simt_vs_oracle(lens, H, dtype):
-    _attn_case(lens, H, 16, dtype, impl=1, tol_out=1e-3, tol_grad=1e-3)
+    # bf16 gradients: delta = sum(dout*out) is taken from the saved bf16 output (the flash-attn contract), which alone
+    # contributes ~2e-3 relative; fp16 keeps 1e-3.
+    _attn_case(lens, H, 16, dtype, impl=1, tol_out=1e-3, tol_grad=1e-3 if dtype == torch.float16 else 4e-3)
 
 
 def test_patch_attention_simt_other_head_dims():
-    _attn_case([256, 100], 2, 32, torch.bfloat16, impl=1, tol_out=1e-3, tol_grad=1e-3)
+    _attn_case([256, 100], 2, 32, torch.bfloat16, impl=1, tol_out=1e-3, tol_grad=4e-3)
     _attn_case([200], 1, 64, torch.float16, impl=1, tol_out=1e-3, tol_grad=1e-3)
 
 

@@ -221,8 +221,8 @@ inline bool attn_umma_supported(int dtype, int head_dim) {
 inline int attn_block_n() {
   static int bn = [] {
     const char* e = getenv("B2PC_ATTN_BN");
-    int v = e ? atoi(e) : 128;
-    return v == 64 ? 64 : 128;
+    int v = e ? atoi(e) : 64;
+    return v == 128 ? 128 : 64;
   }();
   return bn;
 }

@@ -1,13 +1,210 @@
-// tcgen05 implicit-GEMM sparse convolution (placeholder until the kernel lands: reports "unsupported" so the
-// dispatcher keeps using the SIMT kernels).
+// Sparse convolution as an output-stationary implicit GEMM on tcgen05 tensor cores.
+//
+//   out[j, :] = bias + sum_k  feat[pair[k', j], :] @ W_k            (k' = flip ? KV-1-k : k)
+//
+// One CTA owns 128 consecutive output rows x n_tile output channels; the fp32 accumulator [128 x n_tile] lives in
+// TMEM for the whole sweep over kernel offsets.  Per (active offset k, channel chunk of KC): thread t gathers row
+// pair[k', row0+t] (KC*2 contiguous bytes, zero-filled when the pair is absent) into a K-major operand tile with
+// cp.async, the matching W_k slice is staged next to it, and one thread issues KC/16 tcgen05.mma (M=128, N=n_tile,
+// K=16).  Offsets with no partner in the whole tile are skipped.  A ring of stages keeps several gathers in flight
+// while the tensor core drains earlier ones; stage reuse is gated by tcgen05.commit -> mbarrier.
+// No atomics: every output element is written once, deterministically.
 #pragma once
 #include "common.cuh"
+#include "umma.cuh"
+#include "attn_umma.cuh"  // UmmaFmt, pack2
 
 namespace b2pc {
-inline bool spconv_umma_supported(int, int, int) { return false; }
-inline int launch_gather_gemm_umma(const void*, const void*, const void*, const int32_t*, int64_t, int64_t, int64_t, int, int, int,
-                                   int, int, int, void*, cudaStream_t) {
-  set_error("spconv_gather_gemm: tcgen05 kernel not built");
-  return B2PC_ERR_UNSUPPORTED;
+
+constexpr int kCuM = 128;       // output rows per CTA (= threads)
+constexpr int kCuMaxKV = 32;    // kernel volume limit of this path (27 for 3^3, 8 for 2^3)
+constexpr int kCuMaxStages = 4;
+
+struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes; };
+
+inline ConvUmmaCfg conv_umma_cfg(int c_in, int c_out) {
+  ConvUmmaCfg c;
+  c.kc = c_in % 64 == 0 ? 64 : (c_in % 32 == 0 ? 32 : 16);
+  c.n_tile = c_out <= 256 ? c_out : (c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64));
+  c.tmem_cols = 32;
+  while (c.tmem_cols < c.n_tile) c.tmem_cols <<= 1;
+  const int stage_bytes = kCuM * c.kc * 2 + c.n_tile * c.kc * 2;
+  c.stages = stage_bytes <= 24 * 1024 ? 4 : 3;
+  c.smem_bytes = kCuMaxKV * kCuM * 4 + 256 + c.stages * stage_bytes;
+  return c;
 }
+
+inline bool spconv_umma_supported(int dtype, int c_in, int c_out) {
+  if (dtype != B2PC_F16 && dtype != B2PC_BF16) return false;
+  if (c_in % 16 != 0 || c_out % 16 != 0) return false;
+  if (c_out > 256 && c_out % 64 != 0) return false;
+  return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCuM)
+gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
+                        const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
+                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols) {
+  using namespace umma;
+  extern __shared__ __align__(128) uint8_t smem[];
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                       // [kCuMaxKV][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCuMaxKV * kCuM * 4);  // [kCuMaxStages]
+  uint32_t* mask_s = reinterpret_cast<uint32_t*>(bars + kCuMaxStages);
+  uint32_t* tmem_slot = mask_s + 1;
+  uint8_t* stage0 = smem + kCuMaxKV * kCuM * 4 + 256;
+  const int a_bytes = kCuM * kc * 2, b_bytes = n_tile * kc * 2, stage_bytes = a_bytes + b_bytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kCuM;
+  const int n0 = blockIdx.y * n_tile;
+
+  if (warp == 0) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  if (tid == 0) {
+    for (int s = 0; s < kCuMaxStages; ++s) mbar_init(&bars[s], 1);
+    *mask_s = 0;
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // rulebook slice of this tile + which offsets have any partner at all
+  {
+    const int64_t j = row0 + tid;
+    for (int k = 0; k < kv; ++k) {
+      const int kp = flip ? kv - 1 - k : k;
+      const int32_t v = (j < n_out) ? pair[(int64_t)kp * pair_stride + j] : -1;
+      idx_s[k * kCuM + tid] = v;
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, v >= 0);
+      if (lane == 0 && b) atomicOr(mask_s, 1u << k);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t mask = *mask_s;
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_act = __popc(mask);
+  const int n_cc = c_in / kc;
+  const int n_it = n_act * n_cc;
+  const uint32_t idesc = make_idesc(128, n_tile, UmmaFmt<T>::v, UmmaFmt<T>::v, 0, transpose_w ? 1 : 0);
+
+  auto issue_loads = [&](int it) {
+    const int s = it % stages;
+    uint8_t* a_s = stage0 + s * stage_bytes;
+    uint8_t* b_s = a_s + a_bytes;
+    const int k = __fns(mask, 0, it / n_cc + 1);
+    const int c0 = (it % n_cc) * kc;
+    // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16
+    const int32_t src = idx_s[k * kCuM + tid];
+    const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + c0;
+    const uint32_t a_dst = smem_u32(a_s) + tid * 16;
+    for (int p = 0; p < kc / 8; ++p) cp_async16(a_dst + p * (kCuM * 16), g + p * 8, src >= 0);
+    // B: W_k slice
+    if (!transpose_w) {
+      // K-major: rows n (c_out side), kc contiguous channels; piece (n, p) -> p*(n_tile*16) + n*16
+      const int ppr = kc / 8;
+      for (int q = tid; q < n_tile * ppr; q += kCuM) {
+        const int n = q / ppr, p = q % ppr;
+        cp_async16(smem_u32(b_s) + p * (n_tile * 16) + n * 16, weight + ((int64_t)(n0 + n) * kv + k) * c_in + c0 + p * 8, true);
+      }
+    } else {
+      // MN-major: rows kk (reduction side = weight's c_out axis), n_tile contiguous; piece (kk, p) -> p*(kc*16) + kk*16
+      const int ppr = n_tile / 8;
+      for (int q = tid; q < kc * ppr; q += kCuM) {
+        const int kk = q / ppr, p = q % ppr;
+        cp_async16(smem_u32(b_s) + p * (kc * 16) + kk * 16, weight + ((int64_t)(c0 + kk) * kv + k) * c_out + n0 + p * 8, true);
+      }
+    }
+  };
+
+  const int PD = stages - 1;  // prefetch distance
+  for (int it = 0; it < PD; ++it) {
+    if (it < n_it) issue_loads(it);
+    cp_async_commit();
+  }
+  for (int it = 0; it < n_it; ++it) {
+    // refill: iteration it+PD goes into the stage last used by iteration it+PD-stages = it-1
+    const int nx = it + PD;
+    if (nx < n_it) {
+      if (it >= 1) mbar_wait(&bars[(it - 1) % stages], ((it - 1) / stages) & 1);
+      issue_loads(nx);
+    }
+    cp_async_commit();
+    // groups committed: PD + it + 1; iteration `it` is group #it  ->  allow PD pending
+    if (PD == 3) cp_async_wait<3>(); else cp_async_wait<2>();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const int s = it % stages;
+      const uint32_t a_addr = smem_u32(stage0 + s * stage_bytes), b_addr = a_addr + a_bytes;
+      for (int ks = 0; ks < kc / 16; ++ks) {
+        const uint64_t da = make_smem_desc(a_addr + 2 * ks * (kCuM * 16), kCuM * 16, 128);
+        const uint64_t db = transpose_w ? make_smem_desc(b_addr + ks * 256, 128, kc * 16)
+                                        : make_smem_desc(b_addr + 2 * ks * (n_tile * 16), n_tile * 16, 128);
+        mma_ss(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+      }
+      mma_commit(&bars[s]);
+    }
+  }
+  if (n_it > 0) mbar_wait(&bars[(n_it - 1) % stages], ((n_it - 1) / stages) & 1);
+  tc_fence_after();
+  // epilogue: thread = row, 16 columns at a time
+  const int64_t j = row0 + tid;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int cb = 0; cb < n_tile; cb += 16) {
+    uint32_t r[16];
+    if (n_it > 0) {
+      tmem_ld16(lane_base + cb, r);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = 0;
+    }
+    if (j < n_out) {
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
+        if (bias) { v0 += to_f32(bias[n0 + cb + 2 * i]); v1 += to_f32(bias[n0 + cb + 2 * i + 1]); }
+        w[i] = pack2<T>(v0, v1);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + j * c_out + n0 + cb);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+template <typename T>
+inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const void* bias, const int32_t* pair,
+                                     int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip,
+                                     void* out, cudaStream_t stream) {
+  const ConvUmmaCfg c = conv_umma_cfg(c_in, c_out);
+  static int max_smem_set = 0;
+  if (c.smem_bytes > max_smem_set) {
+    cudaFuncSetAttribute(gather_gemm_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+    max_smem_set = c.smem_bytes;
+  }
+  dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile);
+  gather_gemm_umma_kernel<T><<<grid, kCuM, c.smem_bytes, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair,
+                                                                   pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,
+                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("spconv_gather_gemm(tcgen05)");
+  return B2PC_OK;
+}
+
+inline int launch_gather_gemm_umma(const void* feat, const void* weight, const void* bias, const int32_t* pair, int64_t pair_stride,
+                                   int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, int dtype,
+                                   void* out, cudaStream_t stream) {
+  (void)n_in;
+  if (n_out == 0) return B2PC_OK;
+  if (dtype == B2PC_BF16)
+    return launch_gather_gemm_umma_t<__nv_bfloat16>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream);
+  return launch_gather_gemm_umma_t<__half>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream);
+}
+
 }  // namespace b2pc

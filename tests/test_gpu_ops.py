@@ -291,3 +291,48 @@ def test_patch_attention_against_flash_attn_if_present():
     out.backward(dout)
     assert rel_l2(out.detach().float(), ref.detach().float()) < 4e-3
     assert rel_l2(qkv.grad.float(), gref.float()) < 8e-3
+
+
+# ---- tcgen05 kernels (impl=2): same oracles, plus A/B against the SIMT kernels at full size ---------------------------
+@pytest.mark.parametrize("lens,H", [([1024], 2), ([1024, 1024, 1024], 4), ([48, 48, 48], 2), ([700], 2), ([1024, 333, 1, 129, 128], 3),
+                                    ([2048, 100], 1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_patch_attention_tcgen05_vs_oracle(lens, H, dtype):
+    # P is rounded to the MMA operand type (bf16: 8 bits) before PV: 3e-3 on the output for bf16, 1e-3 for fp16
+    _attn_case(lens, H, 16, dtype, impl=2, tol_out=3e-3 if dtype == torch.bfloat16 else 1e-3,
+               tol_grad=6e-3 if dtype == torch.bfloat16 else 2e-3)
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (64, 64), (96, 96), (128, 64), (16, 48), (256, 256), (384, 256), (512, 512)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_subm_conv_tcgen05_vs_oracle(cin, cout, dtype):
+    idx = _voxels_16(0.3 if cin <= 128 else 0.08, 1)
+    _conv_case(idx, [112, 112, 112], cin, cout, 3, dtype, 0, impl=2)
+
+
+def test_subm_conv_tcgen05_tile_edges():
+    _conv_case(_voxels_16(1.0, 1), [16, 16, 16], 32, 64, 3, torch.float16, 1, impl=2, bias=False)   # dense cube, 32 full tiles
+    _conv_case(_voxels_16(0.031, 3), [112] * 3, 64, 64, 3, torch.bfloat16, 2, impl=2)               # fewer rows than one tile
+    _conv_case(_voxels_16(0.3, 5, 3), [112] * 3, 64, 32, (3, 1, 3), torch.float16, 3, impl=2)        # KV = 9, batch 3
+
+
+def test_tcgen05_matches_simt_at_scannet_scale():
+    torch.manual_seed(0)
+    b = synth.make_batch(1, seed=4)
+    n = len(b["grid_coord"])
+    idx = torch.from_numpy(np.concatenate([np.zeros((n, 1)), b["grid_coord"]], 1).astype(np.int32)).to(DEV)
+    pair = ops.rulebook_subm(idx, (b["grid_coord"].max(0) + 96).tolist(), 3)
+    feat = torch.randn(n, 64, device=DEV).bfloat16().requires_grad_(True)
+    w = (torch.randn(64, 27, 64, device=DEV) * 0.04).requires_grad_(True)
+    bias = torch.randn(64, device=DEV).requires_grad_(True)
+    dout = torch.randn(n, 64, device=DEV).bfloat16()
+    res = {}
+    for impl in (1, 2):
+        ops.set_impl(impl)
+        feat.grad = w.grad = bias.grad = None
+        out = ops.sparse_conv(feat, w, bias, pair, pair, True)
+        out.backward(dout)
+        res[impl] = (out.detach().float(), feat.grad.float().clone(), w.grad.clone())
+    ops.set_impl(0)
+    for a, b_ in zip(res[1], res[2]):
+        assert rel_l2(b_, a) < 2e-3

@@ -265,14 +265,277 @@ inline int launch_attn_fwd_umma(const void* qkv, int dtype, const int32_t* cu, i
                   : launch_attn_fwd_umma_t<__half, 128>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, stream);
 }
 
-// backward: SIMT kernels until the tcgen05 backward lands
-inline size_t attn_bwd_umma_workspace_bytes(int64_t t, int H, int D) { return attn_bwd_workspace_bytes(t, H, D); }
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward.  One CTA = one (sequence, head, block of 128 keys); thread t owns key row t (= TMEM lane t) and sweeps the
+// queries in blocks of BQ = 64 columns, everything in the transposed frame so that the CTA-owned dK/dV accumulate in TMEM
+// across the sweep and P / dS never leave the SM:
+//     S^T  = K_j Q_i^T     M=128 N=64 K=16   (A = K_j smem, B = Q_i smem)                 -> TMEM [0,64)
+//     dP^T = V_j dO_i^T    M=128 N=64 K=16   (A = V_j smem, B = dO_i smem)                -> TMEM [64,128)
+//     P^T  = exp2(c S^T - lse2_i),  dS^T = P^T * (dP^T - delta_i)      (registers; bf16/fp16 copies to TMEM + smem)
+//     dV_j += P^T  dO_i    M=128 N=16 K=64   (A = P^T  TMEM [128,160), B = dO_i tile read MN-major)  -> TMEM [192,208)
+//     dK_j += dS^T Q_i     M=128 N=16 K=64   (A = dS^T TMEM [160,192), B = Q_i  tile read MN-major)  -> TMEM [208,224)
+//     dQ_i  = dS   K_j     M=64  N=16 K=128  (A = dS smem MN-major,    B = K_j tile read MN-major)   -> TMEM [224,240)
+// dQ_i partials are added into an fp32 accumulator with vector reductions (red.global.add.v4.f32) and converted at the end.
+// The same shared-memory bytes serve as K-major operand (rows x 16 channels) and as MN-major operand (16 channels x rows):
+// only the descriptor differs.
+constexpr int kAbK = 128;   // keys per CTA (= threads)
+constexpr int kAbQ = 64;    // queries per sweep step
+constexpr int kAbStages = 3;
+constexpr int kAbTmemCols = 256;
+// smem: K_j 4096 | V_j 4096 | dS (A of the dQ MMA) 64x128x2 = 16384 | stages x (Q 2048 | dO 2048 | lse2 256 | delta 256) | bar, slot
+constexpr int kAbStageBytes = 2048 + 2048 + 256 + 256;
+constexpr int kAbSmemBytes = 4096 + 4096 + 16384 + kAbStages * kAbStageBytes + 64;
+
+template <typename T>
+__global__ void __launch_bounds__(kAbK)
+attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, const float* __restrict__ lse,
+                     const float* __restrict__ delta, const int32_t* __restrict__ cu, int64_t t_total, int H, float scale,
+                     T* __restrict__ dqkv, float* __restrict__ dq_acc) {
+  using namespace umma;
+  constexpr int D = 16;
+  constexpr uint32_t COL_S = 0, COL_DP = 64, COL_P = 128, COL_DS = 160, COL_DV = 192, COL_DK = 208, COL_DQ = 224;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* k_s = smem;
+  uint8_t* v_s = smem + 4096;
+  uint8_t* ds_s = smem + 8192;
+  uint8_t* st_s = smem + 8192 + 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(st_s + kAbStages * kAbStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seq = blockIdx.y, h = blockIdx.z;
+  const int64_t s0 = cu[seq];
+  const int len = (int)(cu[seq + 1] - s0);
+  const int k0 = blockIdx.x * kAbK;
+  if (k0 >= len) return;
+  const int nblk = (len + kAbQ - 1) / kAbQ;
+  const int64_t row_stride = (int64_t)3 * H * D;
+
+  if (warp == 0) { tmem_alloc(tmem_slot, kAbTmemCols); tmem_relinquish(); }
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+
+  const T* base_q = qkv + (s0 * 3 + 0) * H * D + h * D;
+  const T* base_k = qkv + (s0 * 3 + 1) * H * D + h * D;
+  const T* base_v = qkv + (s0 * 3 + 2) * H * D + h * D;
+  const T* base_do = dout + s0 * H * D + h * D;
+  const float* base_lse = lse + (int64_t)h * t_total + s0;
+  const float* base_dl = delta + (int64_t)h * t_total + s0;
+  {  // K_j, V_j: thread = key row, two 16-byte pieces each, plane layout (chunk c -> c*2048 + row*16)
+    const bool ok = k0 + tid < len;
+    const T* ks = base_k + (int64_t)(k0 + tid) * row_stride;
+    const T* vs = base_v + (int64_t)(k0 + tid) * row_stride;
+    cp_async16(smem_u32(k_s + tid * 16), ok ? ks : base_k, ok);
+    cp_async16(smem_u32(k_s + 2048 + tid * 16), ok ? ks + 8 : base_k, ok);
+    cp_async16(smem_u32(v_s + tid * 16), ok ? vs : base_k, ok);
+    cp_async16(smem_u32(v_s + 2048 + tid * 16), ok ? vs + 8 : base_k, ok);
+  }
+  auto load_q = [&](int blk, int stage) {
+    uint8_t* st = st_s + stage * kAbStageBytes;
+    const int q0 = blk * kAbQ;
+    {  // 64 rows x 2 chunks of Q and of dO = 256 pieces: thread -> (which, row, chunk)
+      const int which = tid >> 6, r = (tid & 63);
+      const bool ok = q0 + r < len;
+      if (which == 0) {
+        const T* src = base_q + (int64_t)(q0 + r) * row_stride;
+        cp_async16(smem_u32(st + r * 16), ok ? src : base_q, ok);
+        cp_async16(smem_u32(st + 1024 + r * 16), ok ? src + 8 : base_q, ok);
+      } else {
+        const T* src = base_do + (int64_t)(q0 + r) * (H * D);
+        cp_async16(smem_u32(st + 2048 + r * 16), ok ? src : base_do, ok);
+        cp_async16(smem_u32(st + 2048 + 1024 + r * 16), ok ? src + 8 : base_do, ok);
+      }
+      // lse / delta of the 64 queries (4-byte async copies; zero when the query does not exist)
+      const float* g = (which == 0 ? base_lse : base_dl) + q0 + r;
+      cp_async4(smem_u32(st + 4096 + which * 256 + r * 4), ok ? g : base_lse, ok);
+    }
+  };
+  load_q(0, 0);
+  cp_async_commit();
+  if (nblk > 1) load_q(1, 1);
+  cp_async_commit();
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+
+  constexpr uint32_t idesc_s = make_idesc(128, kAbQ, UmmaFmt<T>::v, UmmaFmt<T>::v, 0, 0);   // S^T, dP^T
+  constexpr uint32_t idesc_kv = make_idesc(128, 16, UmmaFmt<T>::v, UmmaFmt<T>::v, 0, 1);    // dV, dK: B MN-major
+  constexpr uint32_t idesc_dq = make_idesc(64, 16, UmmaFmt<T>::v, UmmaFmt<T>::v, 1, 1);     // dQ: A and B MN-major
+  const uint64_t desc_k = make_smem_desc(smem_u32(k_s), 2048, 128);
+  const uint64_t desc_v = make_smem_desc(smem_u32(v_s), 2048, 128);
+  const float c = scale * kLog2e;
+
+  auto flush_dq = [&](int blk) {
+    // dQ partial of query block blk: M=64 accumulator, row r lives in lane (r%16) + 32*(r/16); 16 fp32 columns
+    uint32_t r[16];
+    tmem_ld16(lane_base + COL_DQ, r);
+    tmem_ld_wait();
+    const int qi = blk * kAbQ + warp * 16 + lane;
+    if (lane < 16 && qi < len) {
+      float* dst = dq_acc + ((s0 + qi) * H + h) * D;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        red_add_v4(dst + 4 * i, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                   __uint_as_float(r[4 * i + 3]));
+    }
+  };
+
+  for (int i = 0; i < nblk; ++i) {
+    const int stage = i % kAbStages;
+    uint8_t* st = st_s + stage * kAbStageBytes;
+    cp_async_wait<1>();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_ss(tmem_base + COL_S, desc_k, make_smem_desc(smem_u32(st), kAbQ * 16, 128), idesc_s, 0);
+      mma_ss(tmem_base + COL_DP, desc_v, make_smem_desc(smem_u32(st + 2048), kAbQ * 16, 128), idesc_s, 0);
+      mma_commit(bar);
+    }
+    mbar_wait(bar, i & 1);
+    tc_fence_after();
+    if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages);
+    cp_async_commit();
+    if (i > 0) flush_dq(i - 1);
+    const float* lse_s = reinterpret_cast<const float*>(st + 4096);
+    const float* dl_s = reinterpret_cast<const float*>(st + 4096 + 256);
+#pragma unroll
+    for (int ch = 0; ch < kAbQ / 32; ++ch) {
+      uint32_t s_r[32], dp_r[32];
+      tmem_ld32(lane_base + COL_S + ch * 32, s_r);
+      tmem_ld32(lane_base + COL_DP + ch * 32, dp_r);
+      tmem_ld_wait();
+      uint32_t pp[16], dd[16];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + ch * 32 + g * 4);
+        const float4 d4 = *reinterpret_cast<const float4*>(dl_s + ch * 32 + g * 4);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        float p[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p[e] = ex2(fmaf(__uint_as_float(s_r[g * 4 + e]), c, -lv[e] * kLog2e));
+          ds[e] = p[e] * (__uint_as_float(dp_r[g * 4 + e]) - dv[e]);
+        }
+        pp[g * 2] = pack2<T>(p[0], p[1]);
+        pp[g * 2 + 1] = pack2<T>(p[2], p[3]);
+        dd[g * 2] = pack2<T>(ds[0], ds[1]);
+        dd[g * 2 + 1] = pack2<T>(ds[2], ds[3]);
+      }
+      tmem_st16(lane_base + COL_P + ch * 16, pp);
+      tmem_st16(lane_base + COL_DS + ch * 16, dd);
+      // dS as the (MN-major) A operand of the dQ MMA: 8-query piece p of this key -> p*2048 + key*16
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc)
+        *reinterpret_cast<uint4*>(ds_s + (ch * 4 + pc) * 2048 + tid * 16) =
+            make_uint4(dd[pc * 4], dd[pc * 4 + 1], dd[pc * 4 + 2], dd[pc * 4 + 3]);
+    }
+    tmem_st_wait();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < kAbQ / 16; ++ks) {   // reduction over the 64 queries, 16 per MMA
+        mma_ts(tmem_base + COL_DV, tmem_base + COL_P + ks * 8, make_smem_desc(smem_u32(st + 2048 + ks * 256), 128, kAbQ * 16),
+               idesc_kv, (i > 0 || ks > 0) ? 1u : 0u);
+        mma_ts(tmem_base + COL_DK, tmem_base + COL_DS + ks * 8, make_smem_desc(smem_u32(st + ks * 256), 128, kAbQ * 16), idesc_kv,
+               (i > 0 || ks > 0) ? 1u : 0u);
+      }
+#pragma unroll
+      for (int ks = 0; ks < kAbK / 16; ++ks)     // reduction over the 128 keys
+        mma_ss(tmem_base + COL_DQ, make_smem_desc(smem_u32(ds_s + ks * 256), 128, 2048),
+               make_smem_desc(smem_u32(k_s + ks * 256), 128, 2048), idesc_dq, ks > 0 ? 1u : 0u);
+      if (i == nblk - 1) mma_commit(bar);
+    }
+  }
+  mbar_wait(bar, nblk & 1);
+  tc_fence_after();
+  flush_dq(nblk - 1);
+  {
+    uint32_t rv[16], rk[16];
+    tmem_ld16(lane_base + COL_DV, rv);
+    tmem_ld16(lane_base + COL_DK, rk);
+    tmem_ld_wait();
+    const int ki = k0 + tid;
+    if (ki < len) {
+      uint32_t wv[8], wk[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        wv[e] = pack2<T>(__uint_as_float(rv[2 * e]), __uint_as_float(rv[2 * e + 1]));
+        wk[e] = pack2<T>(__uint_as_float(rk[2 * e]) * scale, __uint_as_float(rk[2 * e + 1]) * scale);
+      }
+      uint4* dk = reinterpret_cast<uint4*>(dqkv + (((s0 + ki) * 3 + 1) * H + h) * D);
+      uint4* dv = reinterpret_cast<uint4*>(dqkv + (((s0 + ki) * 3 + 2) * H + h) * D);
+      dk[0] = make_uint4(wk[0], wk[1], wk[2], wk[3]);
+      dk[1] = make_uint4(wk[4], wk[5], wk[6], wk[7]);
+      dv[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      dv[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kAbTmemCols);
+}
+
+// dqkv[t, 0, h, :] = dq_acc[t, h, :] * scale
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_dq_finish_kernel(const float* __restrict__ dq_acc, int64_t n_rows /* T*H */, int H, float scale, T* __restrict__ dqkv) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int64_t t = i / H;
+  const int h = (int)(i % H);
+  const float4* src = reinterpret_cast<const float4*>(dq_acc + i * 16);
+  uint32_t w[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float4 v = src[e];
+    w[2 * e] = pack2<T>(v.x * scale, v.y * scale);
+    w[2 * e + 1] = pack2<T>(v.z * scale, v.w * scale);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(dqkv + ((t * 3 + 0) * H + h) * 16);
+  dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+inline size_t attn_bwd_umma_workspace_bytes(int64_t t, int H, int D) {
+  (void)D;
+  return align_up((size_t)t * H * sizeof(float), 256) + align_up((size_t)t * H * 16 * sizeof(float), 256) + 256;
+}
+
+template <typename T>
+inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void* out, const float* lse, const int32_t* cu, int n_seq,
+                                  int max_seqlen, int64_t t, int H, float scale, void* dqkv, void* ws, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attn_bwd_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
+    configured = true;
+  }
+  float* delta = (float*)ws;
+  float* dq_acc = (float*)((char*)ws + align_up((size_t)t * H * sizeof(float), 256));
+  attn_delta_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>((const T*)dout, (const T*)out, t, H, 16, delta);
+  cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
+  dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
+  attn_bwd_umma_kernel<T><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, lse, delta, cu, t, H, scale, (T*)dqkv,
+                                                               dq_acc);
+  attn_dq_finish_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>(dq_acc, t * H, H, scale, (T*)dqkv);
+  count_launches(3);
+  B2PC_CHECK_LAUNCH("patch_attn_bwd(tcgen05)");
+  return B2PC_OK;
+}
+
 inline int launch_attn_bwd_umma(const void* dout, const void* qkv, const void* out, const float* lse, int dtype, const int32_t* cu,
                                 int n_seq, int max_seqlen, int64_t t, int H, int D, float scale, void* dqkv, void* ws,
                                 cudaStream_t stream) {
+  (void)D;
+  if (n_seq == 0 || t == 0) return B2PC_OK;
   if (dtype == B2PC_F16)
-    return launch_attn_bwd_simt<__half>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, D, scale, dqkv, ws, stream);
-  return launch_attn_bwd_simt<__nv_bfloat16>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, D, scale, dqkv, ws, stream);
+    return launch_attn_bwd_umma_t<__half>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, scale, dqkv, ws, stream);
+  return launch_attn_bwd_umma_t<__nv_bfloat16>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, scale, dqkv, ws, stream);
 }
 
 }  // namespace b2pc

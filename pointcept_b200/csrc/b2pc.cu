@@ -150,7 +150,12 @@ int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bi
 }
 
 size_t b2pc_spconv_bwd_weight_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
-  return bwd_weight_workspace_bytes(n_out, c_in, c_out, kv);
+  size_t b = bwd_weight_workspace_bytes(n_out, c_in, c_out, kv);
+#ifndef B2PC_NO_UMMA
+  const size_t u = wgrad_umma_workspace_bytes(n_out, c_in, c_out, kv);
+  if (u > b) b = u;
+#endif
+  return b;
 }
 
 int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t* pair, int64_t pair_stride, int64_t n_in,
@@ -158,8 +163,16 @@ int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t*
                            size_t workspace_bytes, int impl, b2pc_stream_t stream) {
   B2PC_CHECK_ARG(feat_in && dout && pair && dweight && workspace, "spconv_bwd_weight: null pointer");
   B2PC_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && kv > 0 && pair_stride >= n_out, "spconv_bwd_weight: bad sizes");
-  (void)impl;
   cudaStream_t s = (cudaStream_t)stream;
+  if (workspace_bytes < b2pc_spconv_bwd_weight_workspace_bytes(n_out, c_in, c_out, kv)) { set_error("spconv_bwd_weight: workspace too small"); return B2PC_ERR_WORKSPACE; }
+#ifndef B2PC_NO_UMMA
+  if (impl != 1 && n_out > 0) {
+    if (wgrad_umma_supported(dtype, c_in, c_out)) return launch_bwd_weight_umma(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dtype, dweight, workspace, s);
+    if (impl == 2) { set_error("spconv_bwd_weight: tcgen05 kernel does not support dtype %d c_in %d c_out %d", dtype, c_in, c_out); return B2PC_ERR_UNSUPPORTED; }
+  }
+#else
+  if (impl == 2) { set_error("spconv_bwd_weight: built without tcgen05 kernels"); return B2PC_ERR_UNSUPPORTED; }
+#endif
   switch (dtype) {
     case B2PC_F32: return launch_bwd_weight_simt<float>(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dweight, workspace, workspace_bytes, s);
     case B2PC_F16: return launch_bwd_weight_simt<__half>(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dweight, workspace, workspace_bytes, s);

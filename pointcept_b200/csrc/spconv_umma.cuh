@@ -208,3 +208,236 @@ inline int launch_gather_gemm_umma(const void* feat, const void* weight, const v
 }
 
 }  // namespace b2pc
+
+namespace b2pc {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:   dW[co, k, ci] = sum_j dout[j, co] * feat[pair[k, j], ci]
+// A CTA owns a group of kernel offsets (as many [M x N] fp32 accumulators as fit in the 512 TMEM columns), an M tile of
+// output channels and an N tile of input channels, and sweeps its share of 64-row tiles of the rulebook.  Per row tile the
+// dout slice is staged once (operand A, MN-major: channels contiguous, rows are the reduction axis) and for every offset
+// with at least one partner in the tile the gathered feature rows are staged as operand B (MN-major as well); 4
+// tcgen05.mma (K = 16 rows each) accumulate into that offset's TMEM slice.  Row-range splits are reduced afterwards in a
+// fixed order (deterministic, no atomics).
+constexpr int kWuRows = 64;      // rulebook rows per step (reduction chunk)
+constexpr int kWuStages = 3;
+
+struct WgradCfg { int m_tile, n_mtiles, n_tile, n_ntiles, g_size, n_groups, n_splits, smem_bytes; };
+
+inline WgradCfg wgrad_cfg(int64_t n_out, int c_in, int c_out, int kv) {
+  WgradCfg c;
+  c.m_tile = c_out <= 64 ? 64 : 128;
+  c.n_mtiles = (c_out + c.m_tile - 1) / c.m_tile;
+  c.n_tile = c_in <= 256 ? c_in : (c_in % 256 == 0 ? 256 : (c_in % 128 == 0 ? 128 : 64));
+  c.n_ntiles = c_in / c.n_tile;
+  int ncol = 32;
+  while (ncol < c.n_tile) ncol <<= 1;          // keep accumulator slices on power-of-two column strides
+  c.g_size = 512 / ncol;
+  if (c.g_size > kv) c.g_size = kv;
+  if (c.g_size > 32) c.g_size = 32;
+  c.n_groups = (kv + c.g_size - 1) / c.g_size;
+  const int64_t tiles = ceil_div(n_out, kWuRows);
+  int64_t sp = ceil_div(2 * kNumSMs, (int64_t)c.n_groups * c.n_mtiles * c.n_ntiles);
+  if (sp > tiles) sp = tiles;
+  if (sp < 1) sp = 1;
+  c.n_splits = (int)sp;
+  c.smem_bytes = 32 * kWuRows * 4 + 256 + kWuRows * c.m_tile * 2 + kWuStages * kWuRows * c.n_tile * 2;
+  return c;
+}
+
+inline bool wgrad_umma_supported(int dtype, int c_in, int c_out) {
+  if (dtype != B2PC_F16 && dtype != B2PC_BF16) return false;
+  if (c_in % 16 != 0 || c_out % 8 != 0) return false;
+  if (c_in > 256 && c_in % 64 != 0) return false;
+  return true;
+}
+
+inline size_t wgrad_umma_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
+  if (c_in % 16 != 0 || c_out % 8 != 0 || (c_in > 256 && c_in % 64 != 0)) return 0;
+  const WgradCfg c = wgrad_cfg(n_out > 0 ? n_out : 1, c_in, c_out, kv);
+  return (size_t)c.n_splits * c_out * kv * c_in * sizeof(float) + 256;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+bwd_weight_umma_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const int32_t* __restrict__ pair,
+                       int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv, float* __restrict__ partial, WgradCfg cfg) {
+  using namespace umma;
+  extern __shared__ __align__(128) uint8_t smem[];
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                        // [32][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32 * kWuRows * 4);    // [kWuStages] stage free, [kWuStages] = tile done
+  uint32_t* mask_s = reinterpret_cast<uint32_t*>(bars + kWuStages + 1);
+  uint32_t* tmem_slot = mask_s + 1;
+  uint8_t* a_s = smem + 32 * kWuRows * 4 + 256;
+  const int a_bytes = kWuRows * cfg.m_tile * 2, b_bytes = kWuRows * cfg.n_tile * 2;
+  uint8_t* b_s0 = a_s + a_bytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int bx = blockIdx.x;
+  const int nt = bx % cfg.n_ntiles; bx /= cfg.n_ntiles;
+  const int mt = bx % cfg.n_mtiles; bx /= cfg.n_mtiles;
+  const int group = bx;
+  const int split = blockIdx.y;
+  const int k_begin = group * cfg.g_size;
+  const int k_cnt = min(cfg.g_size, kv - k_begin);
+  const int co0 = mt * cfg.m_tile, ci0 = nt * cfg.n_tile;
+  const int m_valid = min(cfg.m_tile, c_out - co0);
+  int ncol = 32;
+  while (ncol < cfg.n_tile) ncol <<= 1;
+
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (tid == 0) {
+    for (int s = 0; s <= kWuStages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  // zero the A planes that no dout channel will ever fill (c_out smaller than the M tile)
+  for (int q = tid; q < a_bytes / 16; q += 128) reinterpret_cast<uint4*>(a_s)[q] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc(cfg.m_tile, cfg.n_tile, UmmaFmt<T>::v, UmmaFmt<T>::v, 1, 1);
+
+  const int64_t n_tiles = ceil_div(n_out, kWuRows);
+  uint32_t inited = 0;        // offsets (bit = k - k_begin) whose accumulator holds data
+  uint32_t n_commit[kWuStages] = {0, 0, 0};   // completed uses per B stage (uniform across threads)
+  uint32_t n_tile_commit = 0;
+  int ring = 0;               // next B stage
+
+  for (int64_t t = split; t < n_tiles; t += cfg.n_splits) {
+    const int64_t r0 = t * kWuRows;
+    // (1) previous tile's MMAs must be done before A / idx are overwritten
+    if (n_tile_commit > 0) mbar_wait(&bars[kWuStages], (n_tile_commit - 1) & 1);
+    if (tid == 0) *mask_s = 0;
+    __syncthreads();
+    // (2) rulebook slice + active-offset mask
+    for (int q = tid; q < k_cnt * kWuRows; q += 128) {
+      const int kk = q / kWuRows, r = q % kWuRows;
+      const int64_t j = r0 + r;
+      const int32_t v = j < n_out ? pair[(int64_t)(k_begin + kk) * pair_stride + j] : -1;
+      idx_s[kk * kWuRows + r] = v;
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, v >= 0);   // a warp covers rows of one offset (64 rows = 2 warps)
+      if (lane == 0 && b) atomicOr(mask_s, 1u << kk);
+    }
+    // (3) A = dout rows of this tile: piece (row, chunk p) -> p*1024 + row*16
+    {
+      const int ppr = m_valid / 8;
+      for (int q = tid; q < kWuRows * ppr; q += 128) {
+        const int r = q / ppr, p = q % ppr;
+        const int64_t j = r0 + r;
+        cp_async16(smem_u32(a_s) + p * (kWuRows * 16) + r * 16, dout + (j < n_out ? j : 0) * c_out + co0 + p * 8, j < n_out);
+      }
+      cp_async_commit();
+    }
+    __syncthreads();
+    const uint32_t mask = *mask_s;
+    const int n_act = __popc(mask);
+    // (4) sweep the active offsets with a small ring of gathered-B stages
+    auto gather = [&](int a_i, int stage) {
+      const int kk = __fns(mask, 0, a_i + 1);
+      const int r = tid >> 1, half = tid & 1;
+      const int32_t src = idx_s[kk * kWuRows + r];
+      const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + ci0;
+      const uint32_t dst = smem_u32(b_s0 + stage * b_bytes) + r * 16;
+      for (int p = half; p < cfg.n_tile / 8; p += 2) cp_async16(dst + p * (kWuRows * 16), g + p * 8, src >= 0);
+    };
+    // prologue: up to 2 gathers in flight
+    for (int a_i = 0; a_i < 2; ++a_i) {
+      if (a_i < n_act) {
+        const int s = (ring + a_i) % kWuStages;
+        if (n_commit[s] > 0) mbar_wait(&bars[s], (n_commit[s] - 1) & 1);
+        gather(a_i, s);
+      }
+      cp_async_commit();
+    }
+    for (int a_i = 0; a_i < n_act; ++a_i) {
+      const int s = (ring + a_i) % kWuStages;
+      if (a_i + 2 < n_act) {
+        const int s2 = (ring + a_i + 2) % kWuStages;
+        if (n_commit[s2] > 0) mbar_wait(&bars[s2], (n_commit[s2] - 1) & 1);
+        gather(a_i + 2, s2);
+      }
+      cp_async_commit();
+      cp_async_wait<2>();     // A tile + gather a_i have landed (groups: A, g0, g1, then one per iteration)
+      fence_proxy_async();
+      __syncthreads();
+      const int kk = __fns(mask, 0, a_i + 1);
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s0 + s * b_bytes);
+#pragma unroll
+        for (int ks = 0; ks < kWuRows / 16; ++ks)
+          mma_ss(tmem_base + kk * ncol, make_smem_desc(a_addr + ks * 256, 128, kWuRows * 16),
+                 make_smem_desc(b_addr + ks * 256, 128, kWuRows * 16), idesc, (((inited >> kk) & 1u) || ks > 0) ? 1u : 0u);
+        mma_commit(&bars[s]);
+        if (a_i == n_act - 1) mma_commit(&bars[kWuStages]);
+      }
+      inited |= 1u << kk;
+      n_commit[s] += 1;
+    }
+    if (n_act > 0) n_tile_commit += 1;
+    ring = (ring + n_act) % kWuStages;
+    cp_async_wait<0>();
+  }
+  if (n_tile_commit > 0) mbar_wait(&bars[kWuStages], (n_tile_commit - 1) & 1);
+  tc_fence_after();
+  // epilogue: accumulator row -> partial[split][co][k][ci0 .. ci0+n_tile)
+  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  int row;
+  bool row_ok;
+  if (cfg.m_tile == 128) { row = tid; row_ok = row < m_valid; }
+  else { row = warp * 16 + lane; row_ok = lane < 16 && row < m_valid; }
+  for (int kk = 0; kk < k_cnt; ++kk) {
+    const bool has = (inited >> kk) & 1u;
+    float* dst = partial + (((int64_t)split * c_out + co0 + row) * kv + k_begin + kk) * c_in + ci0;
+    for (int cb = 0; cb < cfg.n_tile; cb += 16) {
+      uint32_t r[16];
+      if (has) {
+        tmem_ld16(lane_base + kk * ncol + cb, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0;
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          reinterpret_cast<float4*>(dst + cb)[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
+                                                                __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <typename T>
+inline int launch_bwd_weight_umma_t(const void* feat, const void* dout, const int32_t* pair, int64_t pair_stride, int64_t n_out,
+                                    int c_in, int c_out, int kv, float* dweight, void* ws, cudaStream_t stream) {
+  const WgradCfg c = wgrad_cfg(n_out, c_in, c_out, kv);
+  static int max_smem_set = 0;
+  if (c.smem_bytes > max_smem_set) {
+    cudaFuncSetAttribute(bwd_weight_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+    max_smem_set = c.smem_bytes;
+  }
+  dim3 grid(c.n_groups * c.n_mtiles * c.n_ntiles, c.n_splits);
+  bwd_weight_umma_kernel<T><<<grid, 128, c.smem_bytes, stream>>>((const T*)feat, (const T*)dout, pair, pair_stride, n_out, c_in, c_out,
+                                                                 kv, (float*)ws, c);
+  const int64_t elems = (int64_t)c_out * kv * c_in;
+  int rb = (int)ceil_div(elems, 256);
+  if (rb > kNumSMs * 8) rb = kNumSMs * 8;
+  reduce_splits_kernel<<<rb, 256, 0, stream>>>((const float*)ws, elems, c.n_splits, dweight);
+  count_launches(2);
+  B2PC_CHECK_LAUNCH("spconv_bwd_weight(tcgen05)");
+  return B2PC_OK;
+}
+
+inline int launch_bwd_weight_umma(const void* feat, const void* dout, const int32_t* pair, int64_t pair_stride, int64_t n_out, int c_in,
+                                  int c_out, int kv, int dtype, float* dweight, void* ws, cudaStream_t stream) {
+  if (dtype == B2PC_BF16)
+    return launch_bwd_weight_umma_t<__nv_bfloat16>(feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dweight, ws, stream);
+  return launch_bwd_weight_umma_t<__half>(feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dweight, ws, stream);
+}
+
+}  // namespace b2pc

@@ -134,7 +134,7 @@ int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bi
   cudaStream_t s = (cudaStream_t)stream;
 #ifndef B2PC_NO_UMMA
   if (impl != 1) {
-    if (spconv_umma_supported(dtype, c_in, c_out) && kv <= kCuMaxKV) return launch_gather_gemm_umma(feat, weight, bias, pair, pair_stride, n_in, n_out, c_in, c_out, kv, transpose_w, flip, dtype, out, s);
+    if (spconv_umma_supported(dtype, c_in, c_out)) return launch_gather_gemm_umma(feat, weight, bias, pair, pair_stride, n_in, n_out, c_in, c_out, kv, transpose_w, flip, dtype, out, s);
     if (impl == 2) { set_error("spconv_gather_gemm: tcgen05 kernel does not support dtype %d c_in %d c_out %d", dtype, c_in, c_out); return B2PC_ERR_UNSUPPORTED; }
   }
 #else

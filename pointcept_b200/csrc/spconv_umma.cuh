@@ -18,19 +18,28 @@ namespace b2pc {
 
 constexpr int kCuM = 128;       // output rows per CTA (= threads)
 constexpr int kCuMaxKV = 32;    // kernel volume limit of this path (27 for 3^3, 8 for 2^3)
-constexpr int kCuMaxStages = 4;
+constexpr int kCuMaxStages = 4;   // ring depth (prefetch distance 2)
 
-struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes; };
+struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes, idx_rows; };
 
-inline ConvUmmaCfg conv_umma_cfg(int c_in, int c_out) {
+inline ConvUmmaCfg conv_umma_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   ConvUmmaCfg c;
   c.kc = c_in % 64 == 0 ? 64 : (c_in % 32 == 0 ? 32 : 16);
-  c.n_tile = c_out <= 256 ? c_out : (c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64));
+  // widest N tile (fewest re-gathers of A) that still yields ~100 CTAs; never narrower than 64 columns
+  const int64_t m_tiles = ceil_div(n_out > 0 ? n_out : 1, kCuM);
+  c.n_tile = 0;
+  for (int nt = c_out <= 256 ? c_out : 256; nt >= 16; nt -= 16) {
+    if (c_out % nt != 0) continue;
+    if (c.n_tile == 0) c.n_tile = nt;                 // widest legal tile
+    if (m_tiles * (c_out / nt) >= 100 || nt <= 64) { c.n_tile = nt; break; }
+    c.n_tile = nt;
+  }
   c.tmem_cols = 32;
   while (c.tmem_cols < c.n_tile) c.tmem_cols <<= 1;
   const int stage_bytes = kCuM * c.kc * 2 + c.n_tile * c.kc * 2;
-  c.stages = stage_bytes <= 24 * 1024 ? 4 : 3;
-  c.smem_bytes = kCuMaxKV * kCuM * 4 + 256 + c.stages * stage_bytes;
+  c.stages = kCuMaxStages;
+  c.idx_rows = kv < kCuMaxKV ? kv : kCuMaxKV;
+  c.smem_bytes = c.idx_rows * kCuM * 4 + 256 + c.stages * stage_bytes;
   return c;
 }
 
@@ -45,14 +54,15 @@ template <typename T>
 __global__ void __launch_bounds__(kCuM)
 gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                         const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
-                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols) {
+                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols, int idx_rows) {
   using namespace umma;
   extern __shared__ __align__(128) uint8_t smem[];
-  int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                       // [kCuMaxKV][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCuMaxKV * kCuM * 4);  // [kCuMaxStages]
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                       // [idx_rows][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + idx_rows * kCuM * 4);  // [kCuMaxStages]
   uint32_t* mask_s = reinterpret_cast<uint32_t*>(bars + kCuMaxStages);
   uint32_t* tmem_slot = mask_s + 1;
-  uint8_t* stage0 = smem + kCuMaxKV * kCuM * 4 + 256;
+  uint8_t* act_s = reinterpret_cast<uint8_t*>(tmem_slot + 1);   // [kCuMaxKV]
+  uint8_t* stage0 = smem + idx_rows * kCuM * 4 + 256;
   const int a_bytes = kCuM * kc * 2, b_bytes = n_tile * kc * 2, stage_bytes = a_bytes + b_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -62,91 +72,113 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   if (warp == 0) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   if (tid == 0) {
     for (int s = 0; s < kCuMaxStages; ++s) mbar_init(&bars[s], 1);
-    *mask_s = 0;
     fence_mbar_init();
-  }
-  __syncthreads();
-  // rulebook slice of this tile + which offsets have any partner at all
-  {
-    const int64_t j = row0 + tid;
-    for (int k = 0; k < kv; ++k) {
-      const int kp = flip ? kv - 1 - k : k;
-      const int32_t v = (j < n_out) ? pair[(int64_t)kp * pair_stride + j] : -1;
-      idx_s[k * kCuM + tid] = v;
-      const unsigned b = __ballot_sync(0xFFFFFFFFu, v >= 0);
-      if (lane == 0 && b) atomicOr(mask_s, 1u << k);
-    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t mask = *mask_s;
   const uint32_t tmem_base = *tmem_slot;
-  const int n_act = __popc(mask);
   const int n_cc = c_in / kc;
-  const int n_it = n_act * n_cc;
   const uint32_t idesc = make_idesc(128, n_tile, UmmaFmt<T>::v, UmmaFmt<T>::v, 0, transpose_w ? 1 : 0);
+  const int PD = stages - 2;  // prefetch distance: a refilled stage was consumed two iterations ago, so its MMAs are (almost
+                              // always) complete already and the stage-free wait does not serialise on the tensor pipe
+  int gi = 0;                 // iterations issued so far (uniform); stage = gi % stages, use count = gi / stages
 
-  auto issue_loads = [&](int it) {
-    const int s = it % stages;
-    uint8_t* a_s = stage0 + s * stage_bytes;
-    uint8_t* b_s = a_s + a_bytes;
-    const int k = __fns(mask, 0, it / n_cc + 1);
-    const int c0 = (it % n_cc) * kc;
-    // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16
-    const int32_t src = idx_s[k * kCuM + tid];
-    const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + c0;
-    const uint32_t a_dst = smem_u32(a_s) + tid * 16;
-    for (int p = 0; p < kc / 8; ++p) cp_async16(a_dst + p * (kCuM * 16), g + p * 8, src >= 0);
-    // B: W_k slice
-    if (!transpose_w) {
-      // K-major: rows n (c_out side), kc contiguous channels; piece (n, p) -> p*(n_tile*16) + n*16
-      const int ppr = kc / 8;
-      for (int q = tid; q < n_tile * ppr; q += kCuM) {
-        const int n = q / ppr, p = q % ppr;
-        cp_async16(smem_u32(b_s) + p * (n_tile * 16) + n * 16, weight + ((int64_t)(n0 + n) * kv + k) * c_in + c0 + p * 8, true);
-      }
-    } else {
-      // MN-major: rows kk (reduction side = weight's c_out axis), n_tile contiguous; piece (kk, p) -> p*(kc*16) + kk*16
-      const int ppr = n_tile / 8;
-      for (int q = tid; q < kc * ppr; q += kCuM) {
-        const int kk = q / ppr, p = q % ppr;
-        cp_async16(smem_u32(b_s) + p * (kc * 16) + kk * 16, weight + ((int64_t)(c0 + kk) * kv + k) * c_out + n0 + p * 8, true);
-      }
-    }
-  };
-
-  const int PD = stages - 1;  // prefetch distance
-  for (int it = 0; it < PD; ++it) {
-    if (it < n_it) issue_loads(it);
-    cp_async_commit();
-  }
-  for (int it = 0; it < n_it; ++it) {
-    // refill: iteration it+PD goes into the stage last used by iteration it+PD-stages = it-1
-    const int nx = it + PD;
-    if (nx < n_it) {
-      if (it >= 1) mbar_wait(&bars[(it - 1) % stages], ((it - 1) / stages) & 1);
-      issue_loads(nx);
-    }
-    cp_async_commit();
-    // groups committed: PD + it + 1; iteration `it` is group #it  ->  allow PD pending
-    if (PD == 3) cp_async_wait<3>(); else cp_async_wait<2>();
-    fence_proxy_async();
+  // kernel offsets are processed in chunks of kCuMaxKV (the rulebook slice of a chunk lives in shared memory)
+  for (int kb = 0; kb < kv; kb += kCuMaxKV) {
+    const int kcnt = min(kCuMaxKV, kv - kb);
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const int s = it % stages;
-      const uint32_t a_addr = smem_u32(stage0 + s * stage_bytes), b_addr = a_addr + a_bytes;
-      for (int ks = 0; ks < kc / 16; ++ks) {
-        const uint64_t da = make_smem_desc(a_addr + 2 * ks * (kCuM * 16), kCuM * 16, 128);
-        const uint64_t db = transpose_w ? make_smem_desc(b_addr + ks * 256, 128, kc * 16)
-                                        : make_smem_desc(b_addr + 2 * ks * (n_tile * 16), n_tile * 16, 128);
-        mma_ss(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+    if (tid == 0) *mask_s = 0;
+    __syncthreads();
+    {
+      const int64_t j = row0 + tid;
+      uint32_t wmask = 0;
+      for (int k8 = 0; k8 < kcnt; k8 += 8) {
+        int32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // 8 independent loads in flight before the first use
+          const int k = k8 + u;
+          const int kp = flip ? kv - 1 - (kb + k) : kb + k;
+          v[u] = (k < kcnt && j < n_out) ? __ldg(pair + (int64_t)kp * pair_stride + j) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k8 + u;
+          if (k < kcnt) {
+            idx_s[k * kCuM + tid] = v[u];
+            if (__ballot_sync(0xFFFFFFFFu, v[u] >= 0)) wmask |= 1u << k;
+          }
+        }
       }
-      mma_commit(&bars[s]);
+      if (lane == 0 && wmask) atomicOr(mask_s, wmask);
     }
+    __syncthreads();
+    const uint32_t mask = *mask_s;
+    const int n_act = __popc(mask);
+    const int n_it = n_act * n_cc;
+    if (tid < n_act) act_s[tid] = (uint8_t)__fns(mask, 0, tid + 1);   // active offsets of this chunk, in order
+    __syncthreads();
+
+    auto issue_loads = [&](int it, int s) {
+      uint8_t* a_s = stage0 + s * stage_bytes;
+      uint8_t* b_s = a_s + a_bytes;
+      const int kl = act_s[it / n_cc];                // offset inside the chunk
+      const int k = kb + kl;                          // weight slice
+      const int c0 = (it % n_cc) * kc;
+      // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16
+      const int32_t src = idx_s[kl * kCuM + tid];
+      const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + c0;
+      const uint32_t a_dst = smem_u32(a_s) + tid * 16;
+      for (int p = 0; p < kc / 8; ++p) cp_async16(a_dst + p * (kCuM * 16), g + p * 8, src >= 0);
+      if (!transpose_w) {
+        // B K-major: rows n (c_out side), kc contiguous channels; piece (n, p) -> p*(n_tile*16) + n*16
+        const int ppr = kc / 8;
+        for (int q = tid; q < n_tile * ppr; q += kCuM) {
+          const int n = q / ppr, p = q % ppr;
+          cp_async16(smem_u32(b_s) + p * (n_tile * 16) + n * 16, weight + ((int64_t)(n0 + n) * kv + k) * c_in + c0 + p * 8, true);
+        }
+      } else {
+        // B MN-major: rows kk (reduction side = weight's c_out axis), n_tile contiguous; piece (kk, p) -> p*(kc*16) + kk*16
+        const int ppr = n_tile / 8;
+        for (int q = tid; q < kc * ppr; q += kCuM) {
+          const int kk = q / ppr, p = q % ppr;
+          cp_async16(smem_u32(b_s) + p * (kc * 16) + kk * 16, weight + ((int64_t)(c0 + kk) * kv + k) * c_out + n0 + p * 8, true);
+        }
+      }
+    };
+    auto stage_free = [&](int g) {   // stage g % stages was last read by the MMAs of global iteration g - stages
+      if (g >= stages) mbar_wait(&bars[g % stages], ((g / stages) - 1) & 1);
+    };
+
+    for (int it = 0; it < PD; ++it) {
+      if (it < n_it) { stage_free(gi + it); issue_loads(it, (gi + it) % stages); }
+      cp_async_commit();
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int nx = it + PD;
+      if (nx < n_it) { stage_free(gi + nx); issue_loads(nx, (gi + nx) % stages); }
+      cp_async_commit();
+      cp_async_wait<2>();   // groups committed: PD + it + 1; iteration `it` is group #it -> PD = 2 may stay pending
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const int s = (gi + it) % stages;
+        const uint32_t a_addr = smem_u32(stage0 + s * stage_bytes), b_addr = a_addr + a_bytes;
+        for (int ks = 0; ks < kc / 16; ++ks) {
+          const uint64_t da = make_smem_desc(a_addr + 2 * ks * (kCuM * 16), kCuM * 16, 128);
+          const uint64_t db = transpose_w ? make_smem_desc(b_addr + ks * 256, 128, kc * 16)
+                                          : make_smem_desc(b_addr + 2 * ks * (n_tile * 16), n_tile * 16, 128);
+          mma_ss(tmem_base, da, db, idesc, (gi + it > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(&bars[s]);
+      }
+    }
+    gi += n_it;
+    cp_async_wait<0>();
   }
-  if (n_it > 0) mbar_wait(&bars[(n_it - 1) % stages], ((n_it - 1) / stages) & 1);
+  const int n_it = gi;
+  if (gi > 0) mbar_wait(&bars[(gi - 1) % stages], ((gi - 1) / stages) & 1);
   tc_fence_after();
   // epilogue: thread = row, 16 columns at a time
   const int64_t j = row0 + tid;
@@ -182,7 +214,7 @@ template <typename T>
 inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const void* bias, const int32_t* pair,
                                      int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip,
                                      void* out, cudaStream_t stream) {
-  const ConvUmmaCfg c = conv_umma_cfg(c_in, c_out);
+  const ConvUmmaCfg c = conv_umma_cfg(n_out, c_in, c_out, kv);
   static int max_smem_set = 0;
   if (c.smem_bytes > max_smem_set) {
     cudaFuncSetAttribute(gather_gemm_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
@@ -191,7 +223,7 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
   dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile);
   gather_gemm_umma_kernel<T><<<grid, kCuM, c.smem_bytes, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair,
                                                                    pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,
-                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols);
+                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows);
   count_launches(1);
   B2PC_CHECK_LAUNCH("spconv_gather_gemm(tcgen05)");
   return B2PC_OK;
@@ -220,9 +252,9 @@ namespace b2pc {
 // tcgen05.mma (K = 16 rows each) accumulate into that offset's TMEM slice.  Row-range splits are reduced afterwards in a
 // fixed order (deterministic, no atomics).
 constexpr int kWuRows = 64;      // rulebook rows per step (reduction chunk)
-constexpr int kWuStages = 3;
+constexpr int kWuStages = 4;
 
-struct WgradCfg { int m_tile, n_mtiles, n_tile, n_ntiles, g_size, n_groups, n_splits, smem_bytes; };
+struct WgradCfg { int m_tile, n_mtiles, n_tile, n_ntiles, g_size, n_groups, n_splits, smem_bytes, tmem_cols; };
 
 inline WgradCfg wgrad_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   WgradCfg c;
@@ -232,12 +264,16 @@ inline WgradCfg wgrad_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   c.n_ntiles = c_in / c.n_tile;
   int ncol = 32;
   while (ncol < c.n_tile) ncol <<= 1;          // keep accumulator slices on power-of-two column strides
-  c.g_size = 512 / ncol;
+  // TMEM budget per CTA: narrow tiles take 128 columns so that four CTAs share an SM (their per-step work is tiny and
+  // latency bound), wide tiles take more columns and rely on the tensor pipe instead
+  c.tmem_cols = ncol <= 64 ? 128 : (ncol == 128 ? 256 : 512);
+  c.g_size = c.tmem_cols / ncol;
   if (c.g_size > kv) c.g_size = kv;
   if (c.g_size > 32) c.g_size = 32;
   c.n_groups = (kv + c.g_size - 1) / c.g_size;
   const int64_t tiles = ceil_div(n_out, kWuRows);
-  int64_t sp = ceil_div(2 * kNumSMs, (int64_t)c.n_groups * c.n_mtiles * c.n_ntiles);
+  const int per_sm = 512 / c.tmem_cols;
+  int64_t sp = ceil_div((int64_t)2 * per_sm * kNumSMs, (int64_t)c.n_groups * c.n_mtiles * c.n_ntiles);
   if (sp > tiles) sp = tiles;
   if (sp < 1) sp = 1;
   c.n_splits = (int)sp;
@@ -285,7 +321,7 @@ bwd_weight_umma_kernel(const T* __restrict__ feat, const T* __restrict__ dout, c
   int ncol = 32;
   while (ncol < cfg.n_tile) ncol <<= 1;
 
-  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, cfg.tmem_cols); tmem_relinquish(); }
   if (tid == 0) {
     for (int s = 0; s <= kWuStages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
@@ -300,7 +336,7 @@ bwd_weight_umma_kernel(const T* __restrict__ feat, const T* __restrict__ dout, c
 
   const int64_t n_tiles = ceil_div(n_out, kWuRows);
   uint32_t inited = 0;        // offsets (bit = k - k_begin) whose accumulator holds data
-  uint32_t n_commit[kWuStages] = {0, 0, 0};   // completed uses per B stage (uniform across threads)
+  uint32_t n_commit[kWuStages] = {0, 0, 0, 0};   // completed uses per B stage (uniform across threads)
   uint32_t n_tile_commit = 0;
   int ring = 0;               // next B stage
 
@@ -409,7 +445,7 @@ bwd_weight_umma_kernel(const T* __restrict__ feat, const T* __restrict__ dout, c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, cfg.tmem_cols);
 }
 
 template <typename T>

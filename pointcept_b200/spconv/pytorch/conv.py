@@ -110,6 +110,12 @@ class SparseConvolution(SparseModule):
                                              self.bias.to(feat.dtype) if self.bias is not None else None)
             return x.replace_feature(out)
         data = self._rulebook(x)
+        if self.in_channels % 16 != 0 and feat.dtype in (torch.float16, torch.bfloat16):
+            # tensor-core tiles want the reduction axis in multiples of 16 channels (e.g. the 6-channel stem): zero-pad
+            # features and weight; autograd slices the gradients back
+            padc = 16 - self.in_channels % 16
+            feat = torch.nn.functional.pad(feat, (0, padc))
+            w = torch.nn.functional.pad(w, (0, padc))
         if self.inverse:
             out = ops.sparse_conv(feat, w, self.bias, data.pair_bwd, data.pair_fwd, False)
             res = SparseConvTensor(out, data.indices, data.spatial_shape, x.batch_size, x.grid, x.voxel_num,

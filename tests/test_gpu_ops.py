@@ -310,6 +310,31 @@ def test_subm_conv_tcgen05_vs_oracle(cin, cout, dtype):
     _conv_case(idx, [112, 112, 112], cin, cout, 3, dtype, 0, impl=2)
 
 
+def test_subm_conv_tcgen05_large_kernel_volume():
+    """5^3 stem geometry (125 offsets > one 32-offset rulebook chunk) on the tensor-core path."""
+    _conv_case(_voxels_16(0.3, 2), [112] * 3, 16, 32, 5, torch.bfloat16, 4, impl=2, bias=False)
+    _conv_case(_voxels_16(0.2, 3, 2), [112] * 3, 32, 48, 5, torch.float16, 5, impl=2)
+
+
+def test_stem_conv_module_pads_odd_channel_counts():
+    from pointcept_b200.spconv import pytorch as spconv
+    torch.manual_seed(0)
+    idx = _voxels_16(0.3, 6)
+    n = len(idx)
+    conv = spconv.SubMConv3d(6, 32, kernel_size=5, padding=1, bias=False, indice_key="stem").to(DEV)
+    feat = torch.randn(n, 6, device=DEV)
+    x = spconv.SparseConvTensor(feat, torch.from_numpy(idx).to(DEV), [112] * 3, 1)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = conv(x).features
+    y.float().square().sum().backward()
+    pair = osp.subm_rulebook(idx, [112] * 3, 5)
+    w64 = conv.weight.detach().cpu().reshape(32, 125, 6).bfloat16().double().requires_grad_(True)
+    ref = osp.conv_apply(feat.cpu().bfloat16().double(), w64, pair)
+    assert rel_l2(y.detach().float(), ref.detach().bfloat16().float()) < 1e-3
+    (ref.bfloat16().double().detach() * 0 + ref).square().sum().backward()
+    assert rel_l2(conv.weight.grad.reshape(32, 125, 6), w64.grad) < 1e-2   # upstream gradient is 2*y in bf16 on the GPU side
+
+
 def test_subm_conv_tcgen05_tile_edges():
     _conv_case(_voxels_16(1.0, 1), [16, 16, 16], 32, 64, 3, torch.float16, 1, impl=2, bias=False)   # dense cube, 32 full tiles
     _conv_case(_voxels_16(0.031, 3), [112] * 3, 64, 64, 3, torch.bfloat16, 2, impl=2)               # fewer rows than one tile

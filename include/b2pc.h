@@ -144,6 +144,19 @@ int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t*
                            float* dweight, void* workspace, size_t workspace_bytes, int impl,
                            b2pc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Glue on the path between the two operators: fused LayerNorm over point
+ * features [N, C] as applied at point_transformer_v3m1_base.py:285,288,300 (nn.LayerNorm under
+ * autocast: fp32 statistics).  x / dx in x_dtype, y / dy in y_dtype, gamma/beta/mean/rstd fp32.
+ * C must be a multiple of 32 and <= 512.
+ * ------------------------------------------------------------------------------------------- */
+int b2pc_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t n, int c,
+                        float eps, void* y, int y_dtype, float* mean, float* rstd, b2pc_stream_t stream);
+size_t b2pc_layer_norm_bwd_workspace_bytes(int64_t n, int c);
+int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype, const float* gamma,
+                        const float* mean, const float* rstd, int64_t n, int c, void* dx, float* dgamma,
+                        float* dbeta, void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 #include "rulebook.cuh"
 #include "spconv_simt.cuh"
 #include "attn_simt.cuh"
+#include "layernorm.cuh"
 #ifndef B2PC_NO_UMMA
 #include "attn_umma.cuh"
 #include "spconv_umma.cuh"
@@ -180,6 +181,23 @@ int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t*
   }
   set_error("spconv_bwd_weight: unknown dtype %d", dtype);
   return B2PC_ERR_INVALID_ARG;
+}
+
+// ---- glue: fused LayerNorm ---------------------------------------------------------------------------------------
+int b2pc_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t n, int c, float eps, void* y,
+                        int y_dtype, float* mean, float* rstd, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(x && gamma && y && mean && rstd, "layer_norm_fwd: null pointer");
+  return launch_layer_norm_fwd(x, x_dtype, gamma, beta, n, c, eps, y, y_dtype, mean, rstd, (cudaStream_t)stream);
+}
+
+size_t b2pc_layer_norm_bwd_workspace_bytes(int64_t n, int c) { return layer_norm_bwd_workspace_bytes(n, c); }
+
+int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
+                        const float* rstd, int64_t n, int c, void* dx, float* dgamma, float* dbeta, void* workspace,
+                        size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && workspace, "layer_norm_bwd: null pointer");
+  return launch_layer_norm_bwd(dy, y_dtype, x, x_dtype, gamma, mean, rstd, n, c, dx, dgamma, dbeta, workspace, workspace_bytes,
+                               (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -304,3 +304,50 @@ class SparseConvFn(torch.autograd.Function):
 
 def sparse_conv(feat, weight, bias, table_fwd, table_bwd, flip_bwd):
     return SparseConvFn.apply(feat, weight, bias, table_fwd, table_bwd, flip_bwd)
+
+
+# ------------------------------------------------------------------------------------------------
+# glue: fused LayerNorm (fp32 statistics; output fp32 under autocast like torch's autocast policy)
+# ------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        _need_cuda(x, weight)
+        x = x.contiguous()
+        n, c = x.shape
+        y = torch.empty((n, c), dtype=out_dtype, device=x.device)
+        mean = torch.empty(n, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        L = _lib.lib()
+        _lib.check(L.b2pc_layer_norm_fwd(_p(x), _DTYPES[x.dtype], _p(w), _p(b), n, c, float(eps), _p(y), _DTYPES[out_dtype], _p(mean),
+                                         _p(rstd), _stream()), "layer_norm_fwd")
+        ctx.save_for_backward(x, w, mean, rstd)
+        ctx.has_bias = bias is not None
+        ctx.pdtype = weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        n, c = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg = torch.empty(c, dtype=torch.float32, device=x.device)
+        db = torch.empty(c, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        L = _lib.lib()
+        ws = _ws(L.b2pc_layer_norm_bwd_workspace_bytes(n, c), x.device)
+        _lib.check(L.b2pc_layer_norm_bwd(_p(dy), _DTYPES[dy.dtype], _p(x), _DTYPES[x.dtype], _p(w), _p(mean), _p(rstd), n, c, _p(dx),
+                                         _p(dg), _p(db), _p(ws), ws.numel(), _stream()), "layer_norm_bwd")
+        return dx, dg.to(ctx.pdtype), (db.to(ctx.pdtype) if db is not None else None), None, None
+
+
+def layer_norm_supported(x, c):
+    return x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and c % 32 == 0 and 32 <= c <= 512
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    """nn.LayerNorm over the last dim of [N, C]; under autocast the result is fp32 (torch's autocast policy for layer_norm)."""
+    out_dtype = torch.float32 if (torch.is_autocast_enabled() or x.dtype == torch.float32) else x.dtype
+    return LayerNormFn.apply(x, weight, bias, eps, out_dtype)

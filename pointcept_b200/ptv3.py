@@ -36,6 +36,15 @@ class DropPath(nn.Module):
         return x * mask
 
 
+class FusedLayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state_dict) whose forward + backward are single fused kernels for [N, C] point features."""
+
+    def forward(self, x):
+        if self.elementwise_affine and len(self.normalized_shape) == 1 and ops.layer_norm_supported(x, self.normalized_shape[0]):
+            return ops.layer_norm(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
 class SerializedAttention(PointModule):
     """ptv3m1:51-222 (flash branch only: RPE / upcast options belong to the non-flash fallback)."""
 
@@ -275,8 +284,12 @@ class PointTransformerV3(PointModule):
                  drop_path=0.3, pre_norm=True, shuffle_orders=True, enable_rpe=False, enable_flash=True,
                  upcast_attention=False, upcast_softmax=False, enc_mode=False, pdnorm_bn=False, pdnorm_ln=False,
                  pdnorm_decouple=True, pdnorm_adaptive=False, pdnorm_affine=True,
-                 pdnorm_conditions=("ScanNet", "S3DIS", "Structured3D")):
+                 pdnorm_conditions=("ScanNet", "S3DIS", "Structured3D"), spatial_reorder=False):
         super().__init__()
+        # spatial_reorder (not a reference option): lay the level-0 points out in memory along the first space-filling
+        # curve so that the rulebook gathers and the [order] / [inverse] gathers of the attention hit nearby cache lines.
+        # Results are permutation-equivalent; the returned feat is restored to the caller's point order.
+        self.spatial_reorder = spatial_reorder
         if pdnorm_bn or pdnorm_ln:
             raise NotImplementedError("PDNorm (multi-dataset prompt training) is outside the PT-v3m1 hot path")
         self.num_stages = len(enc_depths)
@@ -285,7 +298,7 @@ class PointTransformerV3(PointModule):
         assert self.num_stages == len(stride) + 1 == len(enc_channels) == len(enc_num_head) == len(enc_patch_size)
         assert enc_mode or self.num_stages == len(dec_depths) + 1 == len(dec_channels) + 1 == len(dec_num_head) + 1
         bn_layer = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
-        ln_layer, act_layer = nn.LayerNorm, nn.GELU
+        ln_layer, act_layer = FusedLayerNorm, nn.GELU
         self.embedding = Embedding(in_channels, enc_channels[0], norm_layer=bn_layer, act_layer=act_layer)
 
         def make_block(ch, heads, patch, dp, i, s):
@@ -324,11 +337,25 @@ class PointTransformerV3(PointModule):
     def forward(self, data_dict):
         point = Point(data_dict)
         point.serialization(order=self.order, shuffle_orders=self.shuffle_orders)
+        restore = None
+        if self.spatial_reorder:
+            with torch.no_grad():
+                perm, restore = point.serialized_order[0], point.serialized_inverse[0]
+                point.serialized_order = restore[point.serialized_order]      # new row of the p-th point of every order
+                point.serialized_inverse = point.serialized_inverse[:, perm]
+                point.serialized_code = point.serialized_code[:, perm]
+                for k in ("coord", "grid_coord", "batch"):
+                    if k in point:
+                        point[k] = point[k][perm]
+            point.feat = point.feat[perm]
+            point["spatial_perm"] = perm
         point.sparsify()
         point = self.embedding(point)
         point = self.enc(point)
         if not self.enc_mode:
             point = self.dec(point)
+            if restore is not None:
+                point.feat = point.feat[restore]
         return point
 
 

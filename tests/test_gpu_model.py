@@ -68,6 +68,20 @@ def test_ptv3_tiny_vs_cpu_oracle_with_bf16_attention_emulated(golden_dir):
     assert rel_l2(out.detach(), ref.detach()) < 5e-3
 
 
+def test_spatial_reorder_is_permutation_equivalent(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ptv3_tiny.npz"))
+    sd = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}
+    data = dict(coord=torch.from_numpy(g["coord"]).to(DEV), grid_coord=torch.from_numpy(g["grid_coord"]).to(DEV),
+                feat=torch.from_numpy(g["feat"]).to(DEV), offset=torch.from_numpy(g["offset"]).to(DEV))
+    outs = []
+    for flag in (False, True):
+        model = _tiny_model(sd)
+        model.spatial_reorder = flag
+        outs.append(model(dict(data)).feat.detach())
+    # same math, different summation order inside BatchNorm statistics and bf16 attention tiles
+    assert rel_l2(outs[1], outs[0]) < 5e-3
+
+
 def test_ptv3_serialization_tables_bit_exact_through_the_model():
     from oracle import serialization as oser
     from pointcept_b200.structure import Point

@@ -361,3 +361,27 @@ def test_tcgen05_matches_simt_at_scannet_scale():
     ops.set_impl(0)
     for a, b_ in zip(res[1], res[2]):
         assert rel_l2(b_, a) < 2e-3
+
+
+# ---- glue: fused LayerNorm ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("xdt,autocast", [(torch.float32, False), (torch.bfloat16, True), (torch.float32, True), (torch.float16, False)])
+def test_fused_layer_norm_vs_torch(c, xdt, autocast):
+    torch.manual_seed(c)
+    n = 3001
+    x = (torch.randn(n, c, device=DEV) * 2 + 0.5).to(xdt).requires_grad_(True)
+    w = torch.randn(c, device=DEV).requires_grad_(True)
+    b = torch.randn(c, device=DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        y = ops.layer_norm(x, w, b, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    x64 = x.detach().double().requires_grad_(True)
+    w64, b64 = w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(x64, (c,), w64, b64, 1e-5)
+    ref.backward(dy.double())
+    assert y.dtype == (torch.float32 if (autocast or xdt == torch.float32) else xdt)
+    tol = 1e-5 if y.dtype == torch.float32 else 1e-3
+    assert rel_l2(y.detach().float(), ref.detach().to(y.dtype).float()) < tol
+    assert rel_l2(x.grad.float(), x64.grad.to(xdt).float()) < (1e-5 if xdt == torch.float32 else 1e-3)
+    assert rel_l2(w.grad, w64.grad) < 1e-4 and rel_l2(b.grad, b64.grad) < 1e-4

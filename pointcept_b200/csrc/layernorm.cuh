@@ -27,6 +27,7 @@ layer_norm_fwd_kernel(const X* __restrict__ x, const float* __restrict__ gamma, 
 #pragma unroll
   for (int i = 0; i < kLnMaxPerLane; ++i)
     if (i < per) { g[i] = gamma[lane + 32 * i]; b[i] = beta ? beta[lane + 32 * i] : 0.f; }
+#pragma unroll 2
   for (int64_t r = warp_global; r < n; r += n_warps) {
     float v[kLnMaxPerLane];
     float s = 0.f;
@@ -63,6 +64,7 @@ layer_norm_bwd_kernel(const Y* __restrict__ dy, const X* __restrict__ x, const f
   float g[kLnMaxPerLane], ag[kLnMaxPerLane], ab[kLnMaxPerLane];
 #pragma unroll
   for (int i = 0; i < kLnMaxPerLane; ++i) { ag[i] = 0.f; ab[i] = 0.f; if (i < per) g[i] = gamma[lane + 32 * i]; }
+#pragma unroll 2
   for (int64_t r = warp_global; r < n; r += n_warps) {
     const float mu = mean[r], rs = rstd[r];
     float xh[kLnMaxPerLane], dh[kLnMaxPerLane];
@@ -106,20 +108,29 @@ layer_norm_bwd_kernel(const Y* __restrict__ dy, const X* __restrict__ x, const f
   }
 }
 
+// one block per 32 channels; 8 warps stride over the per-block partials, then a fixed-order shared-memory sum
 __global__ void __launch_bounds__(256)
 layer_norm_param_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, int blocks, int c,
                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  float sg = 0.f, sb = 0.f;
-  for (int b = 0; b < blocks; ++b) { sg += part_g[(int64_t)b * c + ch]; sb += part_b[(int64_t)b * c + ch]; }
-  dgamma[ch] = sg;
-  if (dbeta) dbeta[ch] = sb;
+  __shared__ float sg[8][32], sb[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
+  float ag = 0.f, ab = 0.f;
+  for (int b = grp; b < blocks; b += 8) { ag += part_g[(int64_t)b * c + ch]; ab += part_b[(int64_t)b * c + ch]; }
+  sg[grp][lane] = ag; sb[grp][lane] = ab;
+  __syncthreads();
+  if (grp == 0) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tg += sg[w][lane]; tb += sb[w][lane]; }
+    dgamma[ch] = tg;
+    if (dbeta) dbeta[ch] = tb;
+  }
 }
 
 inline int ln_blocks(int64_t n) {
   int64_t b = ceil_div(n, kLnThreads / 32 * 4);
-  if (b > kNumSMs * 8) b = kNumSMs * 8;
+  if (b > kNumSMs * 4) b = kNumSMs * 4;
   return (int)(b < 1 ? 1 : b);
 }
 inline size_t layer_norm_bwd_workspace_bytes(int64_t n, int c) { return (size_t)ln_blocks(n) * c * 2 * sizeof(float) + 256; }
@@ -159,7 +170,7 @@ inline int launch_layer_norm_bwd(const void* dy, int yd, const void* x, int xd, 
     return B2PC_OK;
   }
   B2PC_LN_DISPATCH(xd, yd, (layer_norm_bwd_kernel<X, Y><<<blocks, kLnThreads, 0, stream>>>((const Y*)dy, (const X*)x, gamma, mean, rstd, n, c, (X*)dx, pg, pb)));
-  layer_norm_param_reduce_kernel<<<(c + 255) / 256, 256, 0, stream>>>(pg, pb, blocks, c, dgamma, dbeta);
+  layer_norm_param_reduce_kernel<<<c / 32, 256, 0, stream>>>(pg, pb, blocks, c, dgamma, dbeta);
   count_launches(2);
   B2PC_CHECK_LAUNCH("layer_norm_bwd");
   return B2PC_OK;

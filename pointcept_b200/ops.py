@@ -347,7 +347,13 @@ def layer_norm_supported(x, c):
     return x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and c % 32 == 0 and 32 <= c <= 512
 
 
-def layer_norm(x, weight, bias, eps=1e-5):
-    """nn.LayerNorm over the last dim of [N, C]; under autocast the result is fp32 (torch's autocast policy for layer_norm)."""
-    out_dtype = torch.float32 if (torch.is_autocast_enabled() or x.dtype == torch.float32) else x.dtype
+def layer_norm(x, weight, bias, eps=1e-5, emit_autocast_dtype=False):
+    """nn.LayerNorm over the last dim of [N, C]; under autocast the result is fp32 (torch's autocast policy for layer_norm).
+
+    emit_autocast_dtype: the only consumer is an autocast Linear, which would round this fp32 result to the autocast dtype
+    as its first step -- emit that dtype directly (bit-identical values, one cast kernel and 2/3 of the bytes less)."""
+    if torch.is_autocast_enabled():
+        out_dtype = torch.get_autocast_gpu_dtype() if emit_autocast_dtype else torch.float32
+    else:
+        out_dtype = x.dtype
     return LayerNormFn.apply(x, weight, bias, eps, out_dtype)

@@ -39,9 +39,11 @@ class DropPath(nn.Module):
 class FusedLayerNorm(nn.LayerNorm):
     """nn.LayerNorm (same parameters / state_dict) whose forward + backward are single fused kernels for [N, C] point features."""
 
+    emit_autocast_dtype = False   # set on instances whose only consumer is an autocast Linear (pre-norms of attention / MLP)
+
     def forward(self, x):
         if self.elementwise_affine and len(self.normalized_shape) == 1 and ops.layer_norm_supported(x, self.normalized_shape[0]):
-            return ops.layer_norm(x, self.weight, self.bias, self.eps)
+            return ops.layer_norm(x, self.weight, self.bias, self.eps, self.emit_autocast_dtype)
         return super().forward(x)
 
 
@@ -127,6 +129,10 @@ class Block(PointModule):
         self.mlp = PointSequential(MLP(in_channels=channels, hidden_channels=int(channels * mlp_ratio), out_channels=channels,
                                        act_layer=act_layer, drop=proj_drop))
         self.drop_path = PointSequential(DropPath(drop_path) if drop_path > 0.0 else nn.Identity())
+        if pre_norm:
+            for seq in (self.norm1, self.norm2):
+                if isinstance(seq[0], FusedLayerNorm):
+                    seq[0].emit_autocast_dtype = True
 
     def forward(self, point):
         shortcut = point.feat

@@ -133,16 +133,23 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     const int k0 = j * BN;
     const bool tail = (j == nblk - 1) && (len - k0 < BN);
     const int nvalid = len - k0;
-    // pass A: row maximum of this block
+    // S row of this block -> registers once (BN <= 64) or per 32-column chunk twice (BN = 128: max pass, then exp pass)
+    constexpr bool kKeep = BN <= 64;
+    constexpr int NCH = BN / 32;
+    uint32_t sr[kKeep ? NCH : 1][32];
     float mx = -INFINITY;
+    if (kKeep) {
 #pragma unroll
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(lane_base + COL_S + ch * 32, r);
+      for (int ch = 0; ch < NCH; ++ch) tmem_ld32(lane_base + COL_S + ch * 32, sr[ch]);
       tmem_ld_wait();
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      uint32_t (&r)[32] = sr[kKeep ? ch : 0];
+      if (!kKeep) { tmem_ld32(lane_base + COL_S + ch * 32, r); tmem_ld_wait(); }
       if (!tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -154,28 +161,33 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     l *= corr;
 #pragma unroll
     for (int d = 0; d < D; ++d) o[d] *= corr;
-    // pass B: P = exp2(c*S - m_new), row sum, pack to the MMA operand type, store to TMEM
-    float lsum = 0.f;
+    // P = exp2(c*S - m_new), row sum, pack to the MMA operand type, store to TMEM
+    uint64_t lsum2 = pack_f2(0.f, 0.f);
+    const uint64_t c2 = pack_f2(c, c), nm2 = pack_f2(-m_new, -m_new);
 #pragma unroll
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(lane_base + COL_S + ch * 32, r);
-      tmem_ld_wait();
+    for (int ch = 0; ch < NCH; ++ch) {
+      uint32_t (&r)[32] = sr[kKeep ? ch : 0];
+      if (!kKeep) { tmem_ld32(lane_base + COL_S + ch * 32, r); tmem_ld_wait(); }
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), c, -m_new));
-        float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new));
+        float t0, t1;
+        unpack_f2(ffma2(pack_f2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm2), t0, t1);
+        float p0 = ex2(t0), p1 = ex2(t1);
         if (tail) {
           if (ch * 32 + 2 * i >= nvalid) p0 = 0.f;
           if (ch * 32 + 2 * i + 1 >= nvalid) p1 = 0.f;
         }
-        lsum += p0 + p1;
+        lsum2 = fadd2(lsum2, pack_f2(p0, p1));
         pk[i] = pack2<T>(p0, p1);
       }
       tmem_st16(lane_base + COL_P + ch * 16, pk);
     }
-    l += lsum;
+    {
+      float la, lb;
+      unpack_f2(lsum2, la, lb);
+      l += la + lb;
+    }
     m = m_new;
     tmem_st_wait();
     tc_fence_before();
@@ -366,6 +378,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   const uint64_t desc_k = make_smem_desc(smem_u32(k_s), 2048, 128);
   const uint64_t desc_v = make_smem_desc(smem_u32(v_s), 2048, 128);
   const float c = scale * kLog2e;
+  const uint64_t c2 = pack_f2(c, c);
 
   auto flush_dq = [&](int blk) {
     // dQ partial of query block blk: M=64 accumulator, row r lives in lane (r%16) + 32*(r/16); 16 fp32 columns
@@ -410,14 +423,25 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       uint32_t pp[16], dd[16];
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + ch * 32 + g * 4);
-        const float4 d4 = *reinterpret_cast<const float4*>(dl_s + ch * 32 + g * 4);
-        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        // lse_s holds -lse*log2(e), dl_s holds -delta (prepared by attn_delta_kernel): two queries per packed instruction
+        const ulonglong2 l4 = *reinterpret_cast<const ulonglong2*>(lse_s + ch * 32 + g * 4);
+        const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(dl_s + ch * 32 + g * 4);
         float p[4], ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          p[e] = ex2(fmaf(__uint_as_float(s_r[g * 4 + e]), c, -lv[e] * kLog2e));
-          ds[e] = p[e] * (__uint_as_float(dp_r[g * 4 + e]) - dv[e]);
+        {
+          const uint64_t t = ffma2(pack_f2(__uint_as_float(s_r[g * 4]), __uint_as_float(s_r[g * 4 + 1])), c2, l4.x);
+          float t0, t1;
+          unpack_f2(t, t0, t1);
+          p[0] = ex2(t0); p[1] = ex2(t1);
+          unpack_f2(fmul2(pack_f2(p[0], p[1]), fadd2(pack_f2(__uint_as_float(dp_r[g * 4]), __uint_as_float(dp_r[g * 4 + 1])), d4.x)),
+                    ds[0], ds[1]);
+        }
+        {
+          const uint64_t t = ffma2(pack_f2(__uint_as_float(s_r[g * 4 + 2]), __uint_as_float(s_r[g * 4 + 3])), c2, l4.y);
+          float t0, t1;
+          unpack_f2(t, t0, t1);
+          p[2] = ex2(t0); p[3] = ex2(t1);
+          unpack_f2(fmul2(pack_f2(p[2], p[3]), fadd2(pack_f2(__uint_as_float(dp_r[g * 4 + 2]), __uint_as_float(dp_r[g * 4 + 3])), d4.y)),
+                    ds[2], ds[3]);
         }
         pp[g * 2] = pack2<T>(p[0], p[1]);
         pp[g * 2 + 1] = pack2<T>(p[2], p[3]);
@@ -504,7 +528,35 @@ attn_dq_finish_kernel(const float* __restrict__ dq_acc, int64_t n_rows /* T*H */
 
 inline size_t attn_bwd_umma_workspace_bytes(int64_t t, int H, int D) {
   (void)D;
-  return align_up((size_t)t * H * sizeof(float), 256) + align_up((size_t)t * H * 16 * sizeof(float), 256) + 256;
+  return 2 * align_up((size_t)t * H * sizeof(float), 256) + align_up((size_t)t * H * 16 * sizeof(float), 256) + 256;
+}
+
+// ndelta[h, t] = -sum_d dout*out,  nlse2[h, t] = -lse[h, t] * log2(e)   (the signs / scale the main kernel's packed FMAs want)
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const T* __restrict__ dout, const T* __restrict__ out, const float* __restrict__ lse, int64_t t_total, int H,
+                     float* __restrict__ ndelta, float* __restrict__ nlse2) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // over T*H, (t, h) order
+  if (i >= t_total * H) return;
+  const int64_t t = i / H;
+  const int h = (int)(i % H);
+  const uint4* a = reinterpret_cast<const uint4*>(dout + i * 16);
+  const uint4* b = reinterpret_cast<const uint4*>(out + i * 16);
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint4 va = a[q], vb = b[q];
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const T* pa = reinterpret_cast<const T*>(&wa[e]);
+      const T* pb = reinterpret_cast<const T*>(&wb[e]);
+      acc = fmaf(to_f32(pa[0]), to_f32(pb[0]), acc);
+      acc = fmaf(to_f32(pa[1]), to_f32(pb[1]), acc);
+    }
+  }
+  ndelta[(int64_t)h * t_total + t] = -acc;
+  nlse2[(int64_t)h * t_total + t] = -lse[(int64_t)h * t_total + t] * kLog2e;
 }
 
 template <typename T>
@@ -515,12 +567,13 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
     cudaFuncSetAttribute(attn_bwd_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
     configured = true;
   }
-  float* delta = (float*)ws;
-  float* dq_acc = (float*)((char*)ws + align_up((size_t)t * H * sizeof(float), 256));
-  attn_delta_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>((const T*)dout, (const T*)out, t, H, 16, delta);
+  float* delta = (float*)ws;                                                        // holds -delta
+  float* nlse2 = (float*)((char*)ws + align_up((size_t)t * H * sizeof(float), 256));  // holds -lse * log2(e)
+  float* dq_acc = (float*)((char*)ws + 2 * align_up((size_t)t * H * sizeof(float), 256));
+  attn_bwd_prep_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>((const T*)dout, (const T*)out, lse, t, H, delta, nlse2);
   cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
   dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
-  attn_bwd_umma_kernel<T><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, lse, delta, cu, t, H, scale, (T*)dqkv,
+  attn_bwd_umma_kernel<T><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, scale, (T*)dqkv,
                                                                dq_acc);
   attn_dq_finish_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>(dq_acc, t * H, H, scale, (T*)dqkv);
   count_launches(3);

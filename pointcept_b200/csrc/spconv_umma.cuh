@@ -20,7 +20,7 @@ constexpr int kCuM = 128;       // output rows per CTA (= threads)
 constexpr int kCuMaxKV = 32;    // kernel volume limit of this path (27 for 3^3, 8 for 2^3)
 constexpr int kCuMaxStages = 4;   // ring depth (prefetch distance 2)
 
-struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes, idx_rows; };
+struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes, idx_rows, grp; };
 
 inline ConvUmmaCfg conv_umma_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   ConvUmmaCfg c;
@@ -36,10 +36,18 @@ inline ConvUmmaCfg conv_umma_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   }
   c.tmem_cols = 32;
   while (c.tmem_cols < c.n_tile) c.tmem_cols <<= 1;
-  const int stage_bytes = kCuM * c.kc * 2 + c.n_tile * c.kc * 2;
+  const int unit_bytes = kCuM * c.kc * 2 + c.n_tile * c.kc * 2;
+  // narrow layers (one channel chunk per offset): several kernel offsets share one pipeline stage, i.e. one barrier,
+  // one burst of tcgen05.mma and one commit per `grp` offsets instead of per offset
+  c.grp = 1;
+  if (c.kc == c_in) {
+    static const int env_grp = [] { const char* e = getenv("B2PC_CONV_GRP"); return e ? atoi(e) : 0; }();
+    c.grp = env_grp > 0 ? env_grp : 1;   // measured on B200: grouping lowers CTAs/SM and loses (profiles/README.md)
+    if (c.grp > 8) c.grp = 8;
+  }
   c.stages = kCuMaxStages;
   c.idx_rows = kv < kCuMaxKV ? kv : kCuMaxKV;
-  c.smem_bytes = c.idx_rows * kCuM * 4 + 256 + c.stages * stage_bytes;
+  c.smem_bytes = c.idx_rows * kCuM * 4 + 256 + c.stages * c.grp * unit_bytes;
   return c;
 }
 
@@ -54,7 +62,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCuM)
 gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                         const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
-                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols, int idx_rows) {
+                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols, int idx_rows, int grp) {
   using namespace umma;
   extern __shared__ __align__(128) uint8_t smem[];
   int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                       // [idx_rows][128]
@@ -63,7 +71,7 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   uint32_t* tmem_slot = mask_s + 1;
   uint8_t* act_s = reinterpret_cast<uint8_t*>(tmem_slot + 1);   // [kCuMaxKV]
   uint8_t* stage0 = smem + idx_rows * kCuM * 4 + 256;
-  const int a_bytes = kCuM * kc * 2, b_bytes = n_tile * kc * 2, stage_bytes = a_bytes + b_bytes;
+  const int a_bytes = kCuM * kc * 2, b_bytes = n_tile * kc * 2, unit_bytes = a_bytes + b_bytes, stage_bytes = grp * unit_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * kCuM;
@@ -115,16 +123,20 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
     __syncthreads();
     const uint32_t mask = *mask_s;
     const int n_act = __popc(mask);
-    const int n_it = n_act * n_cc;
+    const int n_units = n_act * n_cc;             // unit = (active offset, channel chunk)
+    const int n_it = (n_units + grp - 1) / grp;   // an iteration (= pipeline stage) carries up to grp units
     if (tid < n_act) act_s[tid] = (uint8_t)__fns(mask, 0, tid + 1);   // active offsets of this chunk, in order
     __syncthreads();
 
     auto issue_loads = [&](int it, int s) {
-      uint8_t* a_s = stage0 + s * stage_bytes;
+     for (int u = 0; u < grp; ++u) {
+      const int unit = it * grp + u;
+      if (unit >= n_units) break;
+      uint8_t* a_s = stage0 + s * stage_bytes + u * unit_bytes;
       uint8_t* b_s = a_s + a_bytes;
-      const int kl = act_s[it / n_cc];                // offset inside the chunk
+      const int kl = act_s[unit / n_cc];              // offset inside the chunk
       const int k = kb + kl;                          // weight slice
-      const int c0 = (it % n_cc) * kc;
+      const int c0 = (unit % n_cc) * kc;
       // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16
       const int32_t src = idx_s[kl * kCuM + tid];
       const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + c0;
@@ -145,6 +157,7 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
           cp_async16(smem_u32(b_s) + p * (kc * 16) + kk * 16, weight + ((int64_t)(c0 + kk) * kv + k) * c_out + n0 + p * 8, true);
         }
       }
+     }
     };
     auto stage_free = [&](int g) {   // stage g % stages was last read by the MMAs of global iteration g - stages
       if (g >= stages) mbar_wait(&bars[g % stages], ((g / stages) - 1) & 1);
@@ -164,12 +177,14 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
       if (tid == 0) {
         tc_fence_after();
         const int s = (gi + it) % stages;
-        const uint32_t a_addr = smem_u32(stage0 + s * stage_bytes), b_addr = a_addr + a_bytes;
-        for (int ks = 0; ks < kc / 16; ++ks) {
-          const uint64_t da = make_smem_desc(a_addr + 2 * ks * (kCuM * 16), kCuM * 16, 128);
-          const uint64_t db = transpose_w ? make_smem_desc(b_addr + ks * 256, 128, kc * 16)
-                                          : make_smem_desc(b_addr + 2 * ks * (n_tile * 16), n_tile * 16, 128);
-          mma_ss(tmem_base, da, db, idesc, (gi + it > 0 || ks > 0) ? 1u : 0u);
+        for (int u = 0; u < grp && it * grp + u < n_units; ++u) {
+          const uint32_t a_addr = smem_u32(stage0 + s * stage_bytes + u * unit_bytes), b_addr = a_addr + a_bytes;
+          for (int ks = 0; ks < kc / 16; ++ks) {
+            const uint64_t da = make_smem_desc(a_addr + 2 * ks * (kCuM * 16), kCuM * 16, 128);
+            const uint64_t db = transpose_w ? make_smem_desc(b_addr + ks * 256, 128, kc * 16)
+                                            : make_smem_desc(b_addr + 2 * ks * (n_tile * 16), n_tile * 16, 128);
+            mma_ss(tmem_base, da, db, idesc, (gi + it > 0 || u > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         mma_commit(&bars[s]);
       }
@@ -223,7 +238,7 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
   dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile);
   gather_gemm_umma_kernel<T><<<grid, kCuM, c.smem_bytes, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair,
                                                                    pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,
-                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows);
+                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows, c.grp);
   count_launches(1);
   B2PC_CHECK_LAUNCH("spconv_gather_gemm(tcgen05)");
   return B2PC_OK;

@@ -161,3 +161,54 @@ def _spunet_cpu(sd, b, model):
         for i in range(model.layers[len(model.channels) - s - 1]):
             x = block(x, f"dec.{s}.block{i}", s)
     return F.linear(x, w("final")[:, 0, :], sd["final.bias"])
+
+
+# ---- BASELINE.json configs 3 and 5 at full scene size: size-independent properties -------------------------------------------
+def test_spunet34_scannet_scale_forward_backward_properties():
+    """config 3 shape (SpUNet-v1m1 stock widths) on 2 x 120k-voxel scenes under fp16 autocast (the reference's AMP dtype)."""
+    torch.manual_seed(0)
+    model = SpUNetBase(6, 20).to(DEV).train()
+    b = synth.make_batch(2, seed=31)
+    data = dict(grid_coord=torch.from_numpy(b["grid_coord"]).to(DEV), feat=torch.from_numpy(b["feat"]).to(DEV),
+                offset=torch.from_numpy(b["offset"]).to(DEV))
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = model(data)
+    assert out.shape == (len(b["feat"]), 20) and torch.isfinite(out).all()
+    torch.nn.functional.cross_entropy(out.float(), torch.from_numpy(b["segment"]).to(DEV)).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    # rulebook properties at this size: strided tables are mutually inverse, every input lands in exactly one output
+    from pointcept_b200 import ops
+    bid = np.repeat(np.arange(2), np.diff(b["offset"], prepend=0))
+    idx = torch.from_numpy(np.concatenate([bid[:, None], b["grid_coord"]], 1).astype(np.int32)).to(DEV)
+    shape = (b["grid_coord"].max(0) + 96).tolist()
+    out_idx, oshape, pf, pb = ops.rulebook_strided(idx, shape, 2, 2)
+    n, m = idx.shape[0], out_idx.shape[0]
+    assert int((pb >= 0).sum()) == n and int((pf >= 0).sum()) == n
+    k, i = torch.nonzero(pb >= 0, as_tuple=True)
+    assert torch.equal(pf[k, pb[k, i].long()].long(), i)
+    keys = ((out_idx[:, 0].long() * oshape[0] + out_idx[:, 1]) * oshape[1] + out_idx[:, 2]) * oshape[2] + out_idx[:, 3]
+    assert bool((keys[1:] > keys[:-1]).all())                    # ascending, distinct
+    assert torch.equal(out_idx[pb.max(0).values.long(), 1:], idx[:, 1:] >> 1)
+
+
+def test_ptv3_nuscenes_scale_forward_backward_properties():
+    """config 5 shape: PT-v3m1 base widths, in_channels 4, one ~300k-voxel LiDAR-like sweep (extent > 2^11 -> depth 12)."""
+    from pointcept_b200.ptv3 import PTv3Segmentor, ptv3_base_config
+    from pointcept_b200.structure import Point
+    torch.manual_seed(0)
+    b = synth.make_batch(1, seed=41, kind="lidar")
+    cfg = dict(ptv3_base_config(), in_channels=4)
+    model = PTv3Segmentor(num_classes=16, backbone_out_channels=64, **cfg).to(DEV).train()
+    data = {k: torch.from_numpy(v).to(DEV) for k, v in b.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = model(data)
+    assert out["seg_logits"].shape == (len(b["feat"]), 16) and torch.isfinite(out["seg_logits"]).all()
+    out["loss"].backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    p = Point(grid_coord=data["grid_coord"], offset=data["offset"], feat=data["feat"])
+    p.serialization(order=["z", "z-trans", "hilbert", "hilbert-trans"])
+    assert p.serialized_depth == 12
+    sorted_codes = torch.gather(p.serialized_code, 1, p.serialized_order)
+    assert bool((sorted_codes[:, 1:] > sorted_codes[:, :-1]).all())          # strictly sorted: voxels are unique
+    n = sorted_codes.shape[1]
+    assert torch.equal(torch.gather(p.serialized_inverse, 1, p.serialized_order), torch.arange(n, device=DEV).expand(4, n))

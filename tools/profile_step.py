@@ -41,3 +41,26 @@ tot = sum(e.device_time_total for e in rows)
 print(f"total CUDA kernel time per step: {tot / 2 / 1000:.2f} ms over {sum(e.count for e in rows) // 2} kernels")
 for e in rows[:45]:
     print(f"{e.device_time_total / 2 / 1000:9.3f} ms  {100 * e.device_time_total / tot:5.1f}%  n={e.count // 2:5d}  {e.key[:110]}")
+
+# CPU side: where does the host time of a step go?
+rows_cpu = sorted(ka, key=lambda e: -e.self_cpu_time_total)
+tot_cpu = sum(e.self_cpu_time_total for e in ka)
+print(f"\ntotal self CPU time per step (profiler overhead included): {tot_cpu / 2 / 1000:.1f} ms")
+for e in rows_cpu[:40]:
+    print(f"{e.self_cpu_time_total / 2 / 1000:9.3f} ms  n={e.count // 2:5d}  {e.key[:90]}")
+import cProfile, pstats, io, time
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+print(f"\nwall per step (no profiler): {(time.perf_counter() - t0) / 3 * 1e3:.1f} ms")
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+pr.disable()
+sio = io.StringIO()
+pstats.Stats(pr, stream=sio).sort_stats("tottime").print_stats(35)
+print(sio.getvalue()[:6000])

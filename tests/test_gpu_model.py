@@ -196,7 +196,7 @@ def test_ptv3_nuscenes_scale_forward_backward_properties():
     from pointcept_b200.ptv3 import PTv3Segmentor, ptv3_base_config
     from pointcept_b200.structure import Point
     torch.manual_seed(0)
-    b = synth.make_batch(1, seed=41, kind="lidar")
+    b = synth.make_batch(1, seed=41, kind="lidar", num_classes=16)
     cfg = dict(ptv3_base_config(), in_channels=4)
     model = PTv3Segmentor(num_classes=16, backbone_out_channels=64, **cfg).to(DEV).train()
     data = {k: torch.from_numpy(v).to(DEV) for k, v in b.items()}

@@ -318,8 +318,12 @@ class LayerNormFn(torch.autograd.Function):
         y = torch.empty((n, c), dtype=out_dtype, device=x.device)
         mean = torch.empty(n, dtype=torch.float32, device=x.device)
         rstd = torch.empty(n, dtype=torch.float32, device=x.device)
-        w = weight.detach().float().contiguous()
-        b = bias.detach().float().contiguous() if bias is not None else None
+        w = weight.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        b = bias.detach() if bias is not None else None
+        if b is not None and (b.dtype != torch.float32 or not b.is_contiguous()):
+            b = b.float().contiguous()
         L = _lib.lib()
         _lib.check(L.b2pc_layer_norm_fwd(_p(x), _DTYPES[x.dtype], _p(w), _p(b), n, c, float(eps), _p(y), _DTYPES[out_dtype], _p(mean),
                                          _p(rstd), _stream()), "layer_norm_fwd")
@@ -353,7 +357,7 @@ def layer_norm(x, weight, bias, eps=1e-5, emit_autocast_dtype=False):
     emit_autocast_dtype: the only consumer is an autocast Linear, which would round this fp32 result to the autocast dtype
     as its first step -- emit that dtype directly (bit-identical values, one cast kernel and 2/3 of the bytes less)."""
     if torch.is_autocast_enabled():
-        out_dtype = torch.get_autocast_gpu_dtype() if emit_autocast_dtype else torch.float32
+        out_dtype = torch.get_autocast_dtype("cuda") if emit_autocast_dtype else torch.float32
     else:
         out_dtype = x.dtype
     return LayerNormFn.apply(x, weight, bias, eps, out_dtype)

@@ -174,61 +174,70 @@ class SerializedPooling(PointModule):
         if act_layer is not None:
             self.act = PointSequential(act_layer())
 
-    def forward(self, point):
+    @torch.no_grad()
+    def plan(self, src):
+        """Index side of the pooling (feature independent): clusters, head rows, the pooled level's codes / orders / scene
+        sizes.  `src` needs serialized_code/order/depth, batch, grid_coord, offset (+ host companions).  Contains the only
+        host syncs of the pooling (cluster count, scene sizes), so PointTransformerV3.forward runs all plans up front, when
+        the GPU queue is still empty, instead of stalling in the middle of the feature pipeline."""
         pooling_depth = (math.ceil(self.stride) - 1).bit_length()
-        if pooling_depth > point.serialized_depth:
+        if pooling_depth > src["serialized_depth"]:
             pooling_depth = 0
+        n = src["serialized_code"].shape[1]
+        code = src["serialized_code"] >> pooling_depth * 3
+        order0 = src["serialized_order"][0]
+        sc = code[0][order0]
+        flag = torch.ones_like(sc, dtype=torch.bool)
+        flag[1:] = sc[1:] != sc[:-1]
+        cid_sorted = torch.cumsum(flag, 0) - 1
+        cluster = torch.empty_like(cid_sorted)
+        cluster[order0] = cid_sorted
+        head_pos = torch.nonzero(flag).squeeze(1)                 # host sync: number of clusters
+        head_indices = order0[head_pos]
+        lengths = torch.diff(head_pos, append=head_pos.new_full((1,), n))
+        code = code[:, head_indices]
+        n_scene = len(src["offset"])
+        depth = src["serialized_depth"] - pooling_depth
+        key_bits = 3 * depth + max(n_scene - 1, 1).bit_length()
+        order, inverse = ops.serialize_sort(code, key_bits)
+        if self.shuffle_orders:
+            perm = torch.randperm(code.shape[0]).tolist()
+            code = torch.stack([code[i] for i in perm])
+            order = torch.stack([order[i] for i in perm])
+            inverse = torch.stack([inverse[i] for i in perm])
+        batch = src["batch"][head_indices]
+        counts_host = torch.bincount(batch, minlength=n_scene).tolist()
+        off, acc = [], 0
+        for c in counts_host:
+            acc += c
+            off.append(acc)
+        out = dict(order0=order0, lengths=lengths, head_indices=head_indices, cluster=cluster, pooling_depth=pooling_depth,
+                   serialized_code=code, serialized_order=order, serialized_inverse=inverse, serialized_depth=depth, batch=batch,
+                   grid_coord=src["grid_coord"][head_indices] >> pooling_depth, offset_host=off,
+                   offset=torch.tensor(off, device=batch.device, dtype=src["offset"].dtype))
+        if "grid_max_host" in src:
+            out["grid_max_host"] = [g >> pooling_depth for g in src["grid_max_host"]]
+        return out
+
+    def forward(self, point):
         assert {"serialized_code", "serialized_order", "serialized_inverse", "serialized_depth"}.issubset(point.keys())
-        n = point.feat.shape[0]
-        with torch.no_grad():
-            code = point.serialized_code >> pooling_depth * 3
-            # which row of the (possibly shuffled) code table is sorted by order row 0: all rows work the same way
-            order0 = point.serialized_order[0]
-            sc = code[0][order0]
-            flag = torch.ones_like(sc, dtype=torch.bool)
-            flag[1:] = sc[1:] != sc[:-1]
-            cid_sorted = torch.cumsum(flag, 0) - 1
-            cluster = torch.empty_like(cid_sorted)
-            cluster[order0] = cid_sorted
-            head_pos = torch.nonzero(flag).squeeze(1)                 # host sync: number of clusters
-            m = head_pos.shape[0]
-            head_indices = order0[head_pos]
-            lengths = torch.diff(head_pos, append=head_pos.new_full((1,), n))
-            code = code[:, head_indices]
-            key_bits = 3 * (point.serialized_depth - pooling_depth) + max(len(point.offset) - 1, 1).bit_length()
-            order, inverse = ops.serialize_sort(code, key_bits)
-            if self.shuffle_orders:
-                perm = torch.randperm(code.shape[0]).tolist()
-                code = torch.stack([code[i] for i in perm])
-                order = torch.stack([order[i] for i in perm])
-                inverse = torch.stack([inverse[i] for i in perm])
-            counts_host = None
-            if "offset_host" in point:
-                # scene sizes after pooling: count heads per scene (device) -> host together with nothing else to sync on
-                counts = torch.bincount(point.batch[head_indices], minlength=len(point.offset))
-                counts_host = counts.tolist()
+        pl = point.pop("_pool_plan", None)
+        if pl is None:
+            pl = self.plan(point)
+        order0, lengths = pl["order0"], pl["lengths"]
         feat_sorted = self.proj(point.feat)[order0]
         feat = torch.segment_reduce(feat_sorted, self.reduce, lengths=lengths, axis=0, unsafe=True)
         coord = torch.segment_reduce(point.coord[order0], "mean", lengths=lengths, axis=0, unsafe=True)
-        point_dict = dict(
-            feat=feat, coord=coord, grid_coord=point.grid_coord[head_indices] >> pooling_depth, serialized_code=code,
-            serialized_order=order, serialized_inverse=inverse, serialized_depth=point.serialized_depth - pooling_depth,
-            batch=point.batch[head_indices],
-        )
-        if counts_host is not None:
-            off, acc = [], 0
-            for c in counts_host:
-                acc += c
-                off.append(acc)
-            point_dict["offset_host"] = off
-            point_dict["offset"] = torch.tensor(off, device=feat.device, dtype=point.offset.dtype)
-        if "grid_max_host" in point:
-            point_dict["grid_max_host"] = [g >> pooling_depth for g in point["grid_max_host"]]
+        point_dict = dict(feat=feat, coord=coord)
+        for k in ("grid_coord", "serialized_code", "serialized_order", "serialized_inverse", "serialized_depth", "batch", "offset",
+                  "offset_host", "grid_max_host"):
+            if k in pl:
+                point_dict[k] = pl[k]
         for k in ("condition", "context"):
             if k in point:
                 point_dict[k] = point[k]
         if self.traceable:
-            point_dict["pooling_inverse"] = cluster
+            point_dict["pooling_inverse"] = pl["cluster"]
             point_dict["pooling_parent"] = point
         point = Point(point_dict)
         if getattr(self, "norm", None) is not None:
@@ -356,8 +365,18 @@ class PointTransformerV3(PointModule):
             point.feat = point.feat[perm]
             point["spatial_perm"] = perm
         point.sparsify()
+        # index side of every pooling stage first (their host syncs are cheap while the GPU queue is empty)
+        plans, src = [], point
+        for s in range(1, self.num_stages):
+            pl = getattr(self.enc, f"enc{s}").down.plan(src)
+            plans.append(pl)
+            src = pl
+        point["_pool_plans"] = plans
         point = self.embedding(point)
-        point = self.enc(point)
+        for s in range(self.num_stages):
+            if s > 0:
+                point["_pool_plan"] = plans[s - 1]
+            point = getattr(self.enc, f"enc{s}")(point)
         if not self.enc_mode:
             point = self.dec(point)
             if restore is not None:

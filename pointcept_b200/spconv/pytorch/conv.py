@@ -101,7 +101,7 @@ class SparseConvolution(SparseModule):
         assert isinstance(x, SparseConvTensor)
         feat = x.features
         if torch.is_autocast_enabled():
-            feat = feat.to(torch.get_autocast_gpu_dtype())
+            feat = feat.to(torch.get_autocast_dtype("cuda"))
         kv = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
         w = self.weight.view(self.out_channels, kv, self.in_channels)
         if self.conv1x1 and self.subm:

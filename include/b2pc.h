@@ -145,6 +145,18 @@ int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t*
                            b2pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Serialized pooling: replaces proj(feat)[indices] + torch_scatter.segment_csr(max)
+ * of SerializedPooling.forward (point_transformer_v3m1_base.py:399-421) and its backward.
+ * Cluster s is the run [seg_start[s], seg_start[s]+seg_len[s]) of the sorted sequence `order` (int64 rows).
+ * out [M,C] and x [N,C] in `dtype`; arg [M,C] int32 = winning source row (first maximum).
+ * ------------------------------------------------------------------------------------------- */
+int b2pc_segment_max_fwd(const void* x, int dtype, const int64_t* order, const int64_t* seg_start,
+                         const int64_t* seg_len, int64_t m, int c, void* out, int32_t* arg, b2pc_stream_t stream);
+/* dx [N,C] = scatter of dout [M,C] to the winning rows (dx is zero-filled by the call). */
+int b2pc_segment_max_bwd(const void* dout, int dtype, const int32_t* arg, int64_t m, int c, int64_t n, void* dx,
+                         b2pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Glue on the path between the two operators: fused LayerNorm over point
  * features [N, C] as applied at point_transformer_v3m1_base.py:285,288,300 (nn.LayerNorm under
  * autocast: fp32 statistics).  x / dx in x_dtype, y / dy in y_dtype, gamma/beta/mean/rstd fp32.

@@ -8,6 +8,7 @@
 #include "spconv_simt.cuh"
 #include "attn_simt.cuh"
 #include "layernorm.cuh"
+#include "pool.cuh"
 #ifndef B2PC_NO_UMMA
 #include "attn_umma.cuh"
 #include "spconv_umma.cuh"
@@ -181,6 +182,20 @@ int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t*
   }
   set_error("spconv_bwd_weight: unknown dtype %d", dtype);
   return B2PC_ERR_INVALID_ARG;
+}
+
+// ---- serialized pooling (segment max over runs of the sorted order) --------------------------------------------------------
+int b2pc_segment_max_fwd(const void* x, int dtype, const int64_t* order, const int64_t* seg_start, const int64_t* seg_len, int64_t m,
+                         int c, void* out, int32_t* arg, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(x && order && seg_start && seg_len && out && arg, "segment_max_fwd: null pointer");
+  B2PC_CHECK_ARG(m >= 0 && c > 0, "segment_max_fwd: bad sizes");
+  return launch_segment_max_fwd(x, dtype, order, seg_start, seg_len, m, c, out, arg, (cudaStream_t)stream);
+}
+
+int b2pc_segment_max_bwd(const void* dout, int dtype, const int32_t* arg, int64_t m, int c, int64_t n, void* dx, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(dout && arg && dx, "segment_max_bwd: null pointer");
+  B2PC_CHECK_ARG(m >= 0 && c > 0 && n >= 0, "segment_max_bwd: bad sizes");
+  return launch_segment_max_bwd(dout, dtype, arg, m, c, n, dx, (cudaStream_t)stream);
 }
 
 // ---- glue: fused LayerNorm ---------------------------------------------------------------------------------------

@@ -361,3 +361,61 @@ def layer_norm(x, weight, bias, eps=1e-5, emit_autocast_dtype=False):
     else:
         out_dtype = x.dtype
     return LayerNormFn.apply(x, weight, bias, eps, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# serialized pooling / unpooling (clusters = runs of the order-0 sorted sequence)
+# ------------------------------------------------------------------------------------------------
+class SegmentMaxFn(torch.autograd.Function):
+    """out[m] = max over rows order[start[m] : start[m]+len[m]] of x  -- the [indices] gather, segment_csr(max) and its
+    backward in one kernel each (argmax saved)."""
+
+    @staticmethod
+    def forward(ctx, x, order, seg_start, seg_len):
+        _need_cuda(x, order)
+        x = x.contiguous()
+        n, c = x.shape
+        m = seg_start.shape[0]
+        out = torch.empty((m, c), dtype=x.dtype, device=x.device)
+        arg = torch.empty((m, c), dtype=torch.int32, device=x.device)
+        L = _lib.lib()
+        _lib.check(L.b2pc_segment_max_fwd(_p(x), _DTYPES[x.dtype], _p(order), _p(seg_start), _p(seg_len), m, c, _p(out), _p(arg),
+                                          _stream()), "segment_max_fwd")
+        ctx.save_for_backward(arg)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        m, c = arg.shape
+        dout = dout.contiguous()
+        dx = torch.empty((ctx.n, c), dtype=dout.dtype, device=dout.device)
+        L = _lib.lib()
+        _lib.check(L.b2pc_segment_max_bwd(_p(dout), _DTYPES[dout.dtype], _p(arg), m, c, ctx.n, _p(dx), _stream()), "segment_max_bwd")
+        return dx, None, None, None
+
+
+def segment_max(x, order, seg_start, seg_len):
+    return SegmentMaxFn.apply(x, order, seg_start, seg_len)
+
+
+class UnpoolAddFn(torch.autograd.Function):
+    """out = parent + child[cluster]  (SerializedUnpooling, ptv3m1:479); the gradient of child is a segment sum over the
+    parent's sorted order instead of a sort-based index_put."""
+
+    @staticmethod
+    def forward(ctx, parent, child, cluster, order, seg_len):
+        ctx.save_for_backward(order, seg_len)
+        ctx.dtypes = (parent.dtype, child.dtype)
+        return parent + child.index_select(0, cluster)
+
+    @staticmethod
+    def backward(ctx, dy):
+        order, seg_len = ctx.saved_tensors
+        dchild = torch.segment_reduce(dy.index_select(0, order), "sum", lengths=seg_len, axis=0, unsafe=True)
+        return dy.to(ctx.dtypes[0]), dchild.to(ctx.dtypes[1]), None, None, None
+
+
+def unpool_add(parent, child, cluster, order, seg_len):
+    return UnpoolAddFn.apply(parent, child, cluster, order, seg_len)

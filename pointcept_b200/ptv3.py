@@ -47,6 +47,42 @@ class FusedLayerNorm(nn.LayerNorm):
         return super().forward(x)
 
 
+class _SerializedGather(torch.autograd.Function):
+    """y = x[order_pad]  (rows into patch order, ptv3m1:188).  Every point sits at exactly one primary padded slot
+    (primary_pos) and at most once more as a borrowed filler of its scene's last patch (dup_slots -> dup_points), so the
+    backward is a gather plus a tiny unique-index add -- no sort-based index_put."""
+
+    @staticmethod
+    def forward(ctx, x, order_pad, primary_pos, dup_slots, dup_points):
+        ctx.save_for_backward(primary_pos, dup_slots, dup_points)
+        return x.index_select(0, order_pad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        primary_pos, dup_slots, dup_points = ctx.saved_tensors
+        dx = dy.index_select(0, primary_pos)
+        if dup_slots.numel() > 0:
+            dx.index_add_(0, dup_points, dy.index_select(0, dup_slots))
+        return dx, None, None, None, None
+
+
+class _SerializedScatterBack(torch.autograd.Function):
+    """y = x_pad[primary_pos]  (patch order back to point order, ptv3m1:216); backward writes each row to its unique slot."""
+
+    @staticmethod
+    def forward(ctx, x_pad, primary_pos):
+        ctx.save_for_backward(primary_pos)
+        ctx.t_pad = x_pad.shape[0]
+        return x_pad.index_select(0, primary_pos)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (primary_pos,) = ctx.saved_tensors
+        dx = dy.new_zeros((ctx.t_pad,) + tuple(dy.shape[1:]))
+        dx.index_copy_(0, primary_pos, dy)
+        return dx, None
+
+
 class SerializedAttention(PointModule):
     """ptv3m1:51-222 (flash branch only: RPE / upcast options belong to the non-flash fallback)."""
 
@@ -78,17 +114,29 @@ class SerializedAttention(PointModule):
         key = f"_attn_idx_{self.order_index}"
         if key not in point:
             pad, unpad, _ = self.get_padding_and_inverse(point)
-            point[key] = (point.serialized_order[self.order_index][pad], unpad[point.serialized_inverse[self.order_index]])
+            order_pad = point.serialized_order[self.order_index][pad]
+            primary_pos = unpad[point.serialized_inverse[self.order_index]]
+            # borrowed filler slots of each padded scene: the last K - n%K slots of its padded range (host arithmetic, no sync)
+            K, oh = self.patch_size, point.host_offset()
+            slots, op = [], 0
+            for a, b in zip([0] + list(oh[:-1]), oh):
+                n = b - a
+                npad = ((n + K - 1) // K * K) if n > K else n
+                if npad != n:
+                    slots.append(torch.arange(op + npad - (K - n % K), op + npad, device=pad.device))
+                op += npad
+            dup_slots = torch.cat(slots) if slots else pad.new_zeros(0)
+            point[key] = (order_pad, primary_pos, dup_slots, order_pad[dup_slots])
         return point[key]
 
     def forward(self, point):
         H, K, C = self.num_heads, self.patch_size, self.channels
         _, _, cu_seqlens = self.get_padding_and_inverse(point)
-        order, inverse = self._gather_indices(point)
-        qkv = self.qkv(point.feat)[order]
+        order_pad, primary_pos, dup_slots, dup_points = self._gather_indices(point)
+        qkv = _SerializedGather.apply(self.qkv(point.feat), order_pad, primary_pos, dup_slots, dup_points)
         feat = flash_attn_varlen_qkvpacked_func(qkv.to(torch.bfloat16).reshape(-1, 3, H, C // H), cu_seqlens, max_seqlen=K,
                                                 softmax_scale=self.scale).reshape(-1, C)
-        feat = feat.to(qkv.dtype)[inverse]
+        feat = _SerializedScatterBack.apply(feat.to(qkv.dtype), primary_pos)
         point.feat = self.proj_drop(self.proj(feat))
         return point
 
@@ -211,7 +259,8 @@ class SerializedPooling(PointModule):
         for c in counts_host:
             acc += c
             off.append(acc)
-        out = dict(order0=order0, lengths=lengths, head_indices=head_indices, cluster=cluster, pooling_depth=pooling_depth,
+        out = dict(order0=order0, lengths=lengths, head_pos=head_pos, head_indices=head_indices, cluster=cluster,
+                   pooling_depth=pooling_depth,
                    serialized_code=code, serialized_order=order, serialized_inverse=inverse, serialized_depth=depth, batch=batch,
                    grid_coord=src["grid_coord"][head_indices] >> pooling_depth, offset_host=off,
                    offset=torch.tensor(off, device=batch.device, dtype=src["offset"].dtype))
@@ -225,9 +274,12 @@ class SerializedPooling(PointModule):
         if pl is None:
             pl = self.plan(point)
         order0, lengths = pl["order0"], pl["lengths"]
-        feat_sorted = self.proj(point.feat)[order0]
-        feat = torch.segment_reduce(feat_sorted, self.reduce, lengths=lengths, axis=0, unsafe=True)
-        coord = torch.segment_reduce(point.coord[order0], "mean", lengths=lengths, axis=0, unsafe=True)
+        if self.reduce == "max":
+            feat = ops.segment_max(self.proj(point.feat), order0, pl["head_pos"], lengths)
+        else:
+            feat = torch.segment_reduce(self.proj(point.feat)[order0], self.reduce, lengths=lengths, axis=0, unsafe=True)
+        with torch.no_grad():
+            coord = torch.segment_reduce(point.coord[order0], "mean", lengths=lengths, axis=0, unsafe=True)
         point_dict = dict(feat=feat, coord=coord)
         for k in ("grid_coord", "serialized_code", "serialized_order", "serialized_inverse", "serialized_depth", "batch", "offset",
                   "offset_host", "grid_max_host"):
@@ -239,6 +291,7 @@ class SerializedPooling(PointModule):
         if self.traceable:
             point_dict["pooling_inverse"] = pl["cluster"]
             point_dict["pooling_parent"] = point
+            point_dict["_pool_sorted"] = (order0, lengths)
         point = Point(point_dict)
         if getattr(self, "norm", None) is not None:
             point = self.norm(point)
@@ -266,9 +319,13 @@ class SerializedUnpooling(PointModule):
     def forward(self, point):
         parent = point.pop("pooling_parent")
         inverse = point.pop("pooling_inverse")
+        sorted_info = point.pop("_pool_sorted", None)
         point = self.proj(point)
         parent = self.proj_skip(parent)
-        parent.feat = parent.feat + point.feat[inverse]
+        if sorted_info is not None:
+            parent.feat = ops.unpool_add(parent.feat, point.feat, inverse, sorted_info[0], sorted_info[1])
+        else:
+            parent.feat = parent.feat + point.feat[inverse]
         if self.traceable:
             parent["unpooling_parent"] = point
         return parent

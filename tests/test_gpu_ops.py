@@ -385,3 +385,48 @@ def test_fused_layer_norm_vs_torch(c, xdt, autocast):
     assert rel_l2(y.detach().float(), ref.detach().to(y.dtype).float()) < tol
     assert rel_l2(x.grad.float(), x64.grad.to(xdt).float()) < (1e-5 if xdt == torch.float32 else 1e-3)
     assert rel_l2(w.grad, w64.grad) < 1e-4 and rel_l2(b.grad, b64.grad) < 1e-4
+
+
+# ---- serialized pooling / gathers (8(f).1) -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_segment_max_and_unpool_add_vs_plain_torch(dtype):
+    torch.manual_seed(0)
+    n, c = 5000, 48
+    lens = torch.randint(1, 9, (2000,))
+    lens = lens[torch.cumsum(lens, 0) <= n]
+    lens[-1] += n - int(lens.sum())
+    m = len(lens)
+    start = torch.cumsum(lens, 0) - lens
+    order = torch.randperm(n)
+    cluster = torch.empty(n, dtype=torch.long)
+    cluster[order] = torch.repeat_interleave(torch.arange(m), lens)
+    x = torch.randn(n, c).to(dtype)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.segment_max(xg, order.to(DEV), start.to(DEV), lens.to(DEV))
+    xr = x.float().requires_grad_(True)
+    ref = torch.full((m, c), -float("inf")).scatter_reduce(0, cluster[:, None].expand(-1, c), xr, "amax", include_self=True)
+    assert torch.equal(out.detach().float().cpu(), ref.detach())
+    g = torch.randn(m, c).to(dtype)
+    out.backward(g.to(DEV))
+    # reference gradient: the (first) arg-max row of each cluster/channel receives the gradient
+    xs = x.float()[order]
+    seg = torch.repeat_interleave(torch.arange(m), lens)
+    is_max = xs == ref.detach()[seg]
+    first = torch.zeros_like(is_max)
+    seen = torch.zeros(m, c, dtype=torch.bool)
+    for r in range(n):
+        first[r] = is_max[r] & ~seen[seg[r]]
+        seen[seg[r]] |= is_max[r]
+    want = torch.zeros(n, c)
+    want[order] = first.float() * g.float()[seg]
+    assert torch.equal(xg.grad.float().cpu(), want.to(dtype).float())
+    # unpooling: parent + child[cluster]
+    parent = torch.randn(n, c).to(dtype)
+    child = torch.randn(m, c).to(dtype)
+    pg, cg = parent.to(DEV).requires_grad_(True), child.to(DEV).requires_grad_(True)
+    dy = torch.randn(n, c).to(dtype).to(DEV)
+    ops.unpool_add(pg, cg, cluster.to(DEV), order.to(DEV), lens.to(DEV)).backward(dy)
+    p2, c2 = parent.double().requires_grad_(True), child.double().requires_grad_(True)
+    (p2 + c2[cluster]).backward(dy.double().cpu())
+    assert rel_l2(pg.grad.float(), p2.grad) < 1e-6
+    assert rel_l2(cg.grad.float(), c2.grad) < (1e-6 if dtype == torch.float32 else 5e-3)

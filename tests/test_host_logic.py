@@ -64,6 +64,42 @@ def test_unmodified_reference_models_build_on_the_dropins_with_identical_state_d
         del sys.modules[k]
 
 
+def test_serialized_gather_backward_without_sort_matches_plain_indexing():
+    """The structured backward of the [order] / [inverse] gathers of SerializedAttention (ptv3m1:188,216): pure torch, runs on CPU."""
+    from oracle import padding as opad
+    from pointcept_b200.ptv3 import _SerializedGather, _SerializedScatterBack
+    torch.manual_seed(0)
+    for offset, K in (([5, 17, 20], 4), ([3, 11], 4), ([1024, 2049, 3000], 1024), ([10], 16)):
+        pad, unpad, _ = opad.padding_and_inverse(offset, K)
+        n = offset[-1]
+        order = torch.randperm(n)
+        inverse = torch.empty_like(order)
+        inverse[order] = torch.arange(n)
+        pad, unpad = torch.from_numpy(pad), torch.from_numpy(unpad)
+        order_pad, primary = order[pad], unpad[inverse]
+        slots, op = [], 0
+        for a, b in zip([0] + offset[:-1], offset):
+            cnt = b - a
+            npad = ((cnt + K - 1) // K * K) if cnt > K else cnt
+            if npad != cnt:
+                slots.append(torch.arange(op + npad - (K - cnt % K), op + npad))
+            op += npad
+        dup = torch.cat(slots) if slots else torch.zeros(0, dtype=torch.long)
+        assert torch.equal(order_pad[primary], torch.arange(n))          # every point has one primary slot
+        x = torch.randn(n, 3, requires_grad=True)
+        x2 = x.detach().clone().requires_grad_(True)
+        g = torch.randn(len(pad), 3)
+        _SerializedGather.apply(x, order_pad, primary, dup, order_pad[dup]).backward(g)
+        x2[order_pad].backward(g)
+        assert torch.allclose(x.grad, x2.grad)
+        y = torch.randn(len(pad), 3, requires_grad=True)
+        y2 = y.detach().clone().requires_grad_(True)
+        g2 = torch.randn(n, 3)
+        _SerializedScatterBack.apply(y, primary).backward(g2)
+        y2[primary].backward(g2)
+        assert torch.allclose(y.grad, y2.grad)
+
+
 def _gloo_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))

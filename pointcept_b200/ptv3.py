@@ -406,29 +406,39 @@ class PointTransformerV3(PointModule):
                     dec.add(make_block(dec_channels[s], dec_num_head[s], dec_patch_size[s], dps[i], i, s), name=f"block{i}")
                 self.dec.add(module=dec, name=f"dec{s}")
 
-    def forward(self, data_dict):
+    @torch.no_grad()
+    def prepare(self, data_dict):
+        """Everything of the forward that depends only on coordinates: serialization, optional spatial re-layout, the
+        level-0 sparse tensor and the index plan of every pooling stage (the only host syncs of the model).  Feature
+        independent and gradient free, so a training loop can run it for batch i+1 on a side stream while batch i trains
+        (bench.py does); forward() calls it itself when handed a raw dict."""
         point = Point(data_dict)
         point.serialization(order=self.order, shuffle_orders=self.shuffle_orders)
-        restore = None
         if self.spatial_reorder:
-            with torch.no_grad():
-                perm, restore = point.serialized_order[0], point.serialized_inverse[0]
-                point.serialized_order = restore[point.serialized_order]      # new row of the p-th point of every order
-                point.serialized_inverse = point.serialized_inverse[:, perm]
-                point.serialized_code = point.serialized_code[:, perm]
-                for k in ("coord", "grid_coord", "batch"):
-                    if k in point:
-                        point[k] = point[k][perm]
-            point.feat = point.feat[perm]
-            point["spatial_perm"] = perm
-        point.sparsify()
-        # index side of every pooling stage first (their host syncs are cheap while the GPU queue is empty)
+            perm, restore = point.serialized_order[0], point.serialized_inverse[0]
+            point.serialized_order = restore[point.serialized_order]      # new row of the p-th point of every order
+            point.serialized_inverse = point.serialized_inverse[:, perm]
+            point.serialized_code = point.serialized_code[:, perm]
+            for k in ("coord", "grid_coord", "batch"):
+                if k in point:
+                    point[k] = point[k][perm]
+            point["spatial_perm"], point["spatial_restore"] = perm, restore
         plans, src = [], point
         for s in range(1, self.num_stages):
             pl = getattr(self.enc, f"enc{s}").down.plan(src)
             plans.append(pl)
             src = pl
         point["_pool_plans"] = plans
+        point["_prepared"] = True
+        return point
+
+    def forward(self, data_dict):
+        point = data_dict if isinstance(data_dict, Point) and data_dict.get("_prepared", False) else self.prepare(data_dict)
+        restore = point.get("spatial_restore")
+        if restore is not None:
+            point.feat = point.feat[point["spatial_perm"]]
+        point.sparsify()
+        plans = point["_pool_plans"]
         point = self.embedding(point)
         for s in range(self.num_stages):
             if s > 0:
@@ -449,6 +459,9 @@ class PTv3Segmentor(nn.Module):
         super().__init__()
         self.backbone = PointTransformerV3(**backbone_kwargs)
         self.seg_head = nn.Linear(backbone_out_channels, num_classes) if num_classes > 0 else nn.Identity()
+
+    def prepare(self, input_dict):
+        return self.backbone.prepare(input_dict)
 
     def forward(self, input_dict):
         point = self.backbone(input_dict)

@@ -62,6 +62,21 @@ class Point(dict):
             self["grid_max_host"] = [int(v) for v in self["grid_coord"].max(0).values.tolist()]
         return self["grid_max_host"]
 
+    def record_stream(self, stream):
+        """Mark every tensor reachable from this Point as used on `stream` (tensors made on a side stream, consumed on the
+        training stream: keeps the caching allocator from recycling them early)."""
+        def walk(o):
+            if isinstance(o, torch.Tensor):
+                if o.is_cuda:
+                    o.record_stream(stream)
+            elif isinstance(o, dict):
+                for v in o.values():
+                    walk(v)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    walk(v)
+        walk(self)
+
     def _ensure_grid(self):
         if "grid_coord" not in self:
             assert {"grid_size", "coord"}.issubset(self.keys())

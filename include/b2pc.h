@@ -160,7 +160,7 @@ int b2pc_segment_max_bwd(const void* dout, int dtype, const int32_t* arg, int64_
  * Glue on the path between the two operators: fused LayerNorm over point
  * features [N, C] as applied at point_transformer_v3m1_base.py:285,288,300 (nn.LayerNorm under
  * autocast: fp32 statistics).  x / dx in x_dtype, y / dy in y_dtype, gamma/beta/mean/rstd fp32.
- * C must be a multiple of 32 and <= 512.
+ * C in {32, 64, 128, 256, 512} (the PT-v3 widths).
  * ------------------------------------------------------------------------------------------- */
 int b2pc_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t n, int c,
                         float eps, void* y, int y_dtype, float* mean, float* rstd, b2pc_stream_t stream);

@@ -2,8 +2,7 @@
 // one pass over x per direction, fp32 statistics, any of fp32 / fp16 / bf16 on either side.  HBM-bound:
 // forward reads N*C*sizeof(X) and writes N*C*sizeof(Y) (+8 B/row of statistics); backward reads dy and x once,
 // writes dx once, and reduces dgamma/dbeta through per-block partials (deterministic).
-// A warp owns a row at a time; lane l holds channels l*V .. l*V+V-1 of every 32*V-channel slab (V = 4), so that C = 32
-// still keeps all lanes busy with 1 element... (small C: several rows per warp, see kRowsPerWarp).
+// Lanes own float4 chunks of a row; narrow rows share a warp (C = 32: 4 rows per warp) so every access is coalesced.
 #pragma once
 #include "common.cuh"
 
@@ -12,99 +11,143 @@ namespace b2pc {
 constexpr int kLnThreads = 256;
 constexpr int kLnMaxPerLane = 16;   // C <= 512
 
-template <typename T> __device__ __forceinline__ float ln_load(const T* p, int64_t i) { return to_f32(p[i]); }
+// ---- vector access: 4 consecutive channels per lane -----------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld4<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, float4 v);
+template <> __device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void st4<__half>(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
 
-// rows are distributed over warps; each lane handles channels lane, lane+32, ... (coalesced across the warp)
-template <typename X, typename Y>
+// Mapping: L = min(32, C/4) lanes share a row (each lane owns float4 chunks lane, lane+L, ...: V = C/(4L) of them), so a
+// warp covers 32/L rows with fully coalesced 16-byte (fp32) / 8-byte (16-bit) accesses, and the row reductions are
+// log2(L) shuffles.
+template <typename X, typename Y, int V>
 __global__ void __launch_bounds__(kLnThreads)
 layer_norm_fwd_kernel(const X* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n, int c,
                       float eps, Y* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
-  const int lane = threadIdx.x & 31;
+  const int L = c / (4 * V);             // lanes per row (power of two <= 32)
+  const int rpw = 32 / L;                // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane % L, rin = lane / L;
   const int64_t warp_global = (blockIdx.x * (int64_t)kLnThreads + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * kLnThreads) >> 5;
-  const int per = c >> 5;  // channels per lane (c is a multiple of 32)
-  float g[kLnMaxPerLane], b[kLnMaxPerLane];
+  float4 g[V], b[V];
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i)
-    if (i < per) { g[i] = gamma[lane + 32 * i]; b[i] = beta ? beta[lane + 32 * i] : 0.f; }
-#pragma unroll 2
-  for (int64_t r = warp_global; r < n; r += n_warps) {
-    float v[kLnMaxPerLane];
+  for (int i = 0; i < V; ++i) {
+    g[i] = ld4<float>(gamma + 4 * (sub + i * L));
+    b[i] = beta ? ld4<float>(beta + 4 * (sub + i * L)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_c = 1.f / c;
+  for (int64_t r0 = warp_global * rpw; r0 < n; r0 += n_warps * rpw) {
+    const int64_t r = r0 + rin;
+    const bool ok = r < n;
+    float4 v[V];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i)
-      if (i < per) { v[i] = to_f32(x[r * c + lane + 32 * i]); s += v[i]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-    const float mu = s / c;
+    for (int i = 0; i < V; ++i) {
+      v[i] = ok ? ld4<X>(x + r * c + 4 * (sub + i * L)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    const float mu = s * inv_c;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i)
-      if (i < per) { const float d = v[i] - mu; q += d * d; }
+    for (int i = 0; i < V; ++i) {
+      const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+    const float rs = rsqrtf(q * inv_c + eps);
+    if (ok) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
-    const float rs = rsqrtf(q / c + eps);
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i)
-      if (i < per) y[r * c + lane + 32 * i] = from_f32<Y>((v[i] - mu) * rs * g[i] + b[i]);
-    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+      for (int i = 0; i < V; ++i)
+        st4<Y>(y + r * c + 4 * (sub + i * L),
+               make_float4((v[i].x - mu) * rs * g[i].x + b[i].x, (v[i].y - mu) * rs * g[i].y + b[i].y,
+                           (v[i].z - mu) * rs * g[i].z + b[i].z, (v[i].w - mu) * rs * g[i].w + b[i].w));
+      if (sub == 0) { mean[r] = mu; rstd[r] = rs; }
+    }
   }
 }
 
-template <typename X, typename Y>
+template <typename X, typename Y, int V>
 __global__ void __launch_bounds__(kLnThreads)
 layer_norm_bwd_kernel(const Y* __restrict__ dy, const X* __restrict__ x, const float* __restrict__ gamma,
                       const float* __restrict__ mean, const float* __restrict__ rstd, int64_t n, int c, X* __restrict__ dx,
                       float* __restrict__ part_g, float* __restrict__ part_b) {
-  __shared__ float red[kLnThreads / 32][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  extern __shared__ float red[];         // [2][warps * rpw][c]
+  const int L = c / (4 * V);
+  const int rpw = 32 / L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % L, rin = lane / L;
   const int64_t warp_global = (blockIdx.x * (int64_t)kLnThreads + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * kLnThreads) >> 5;
-  const int per = c >> 5;
-  float g[kLnMaxPerLane], ag[kLnMaxPerLane], ab[kLnMaxPerLane];
+  float4 g[V], ag[V], ab[V];
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) { ag[i] = 0.f; ab[i] = 0.f; if (i < per) g[i] = gamma[lane + 32 * i]; }
-#pragma unroll 2
-  for (int64_t r = warp_global; r < n; r += n_warps) {
-    const float mu = mean[r], rs = rstd[r];
-    float xh[kLnMaxPerLane], dh[kLnMaxPerLane];
+  for (int i = 0; i < V; ++i) {
+    g[i] = ld4<float>(gamma + 4 * (sub + i * L));
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_c = 1.f / c;
+  for (int64_t r0 = warp_global * rpw; r0 < n; r0 += n_warps * rpw) {
+    const int64_t r = r0 + rin;
+    const bool ok = r < n;
+    const float mu = ok ? mean[r] : 0.f, rs = ok ? rstd[r] : 0.f;
+    float4 xh[V], dh[V];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i)
-      if (i < per) {
-        const float d = to_f32(dy[r * c + lane + 32 * i]);
-        xh[i] = (to_f32(x[r * c + lane + 32 * i]) - mu) * rs;
-        dh[i] = d * g[i];
-        s1 += dh[i];
-        s2 += dh[i] * xh[i];
-        ag[i] += d * xh[i];
-        ab[i] += d;
-      }
+    for (int i = 0; i < V; ++i) {
+      const float4 d = ok ? ld4<Y>(dy + r * c + 4 * (sub + i * L)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xv = ok ? ld4<X>(x + r * c + 4 * (sub + i * L)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dh[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+      s1 += (dh[i].x + dh[i].y) + (dh[i].z + dh[i].w);
+      s2 += (dh[i].x * xh[i].x + dh[i].y * xh[i].y) + (dh[i].z * xh[i].z + dh[i].w * xh[i].w);
+      ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o); }
+    const float m1 = s1 * inv_c, m2 = s2 * inv_c;
+    if (ok) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o); }
-    const float m1 = s1 / c, m2 = s2 / c;
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i)
-      if (i < per) dx[r * c + lane + 32 * i] = from_f32<X>(rs * (dh[i] - m1 - xh[i] * m2));
+      for (int i = 0; i < V; ++i)
+        st4<X>(dx + r * c + 4 * (sub + i * L),
+               make_float4(rs * (dh[i].x - m1 - xh[i].x * m2), rs * (dh[i].y - m1 - xh[i].y * m2),
+                           rs * (dh[i].z - m1 - xh[i].z * m2), rs * (dh[i].w - m1 - xh[i].w * m2)));
+    }
   }
-  // block partials: sum over the block's warps, fixed order
-  for (int i = 0; i < per; ++i) {
-    red[warp][lane] = ag[i];
-    __syncthreads();
-    if (warp == 0) {
-      float t = 0.f;
-      for (int w = 0; w < kLnThreads / 32; ++w) t += red[w][lane];
-      part_g[(int64_t)blockIdx.x * c + lane + 32 * i] = t;
-    }
-    __syncthreads();
-    red[warp][lane] = ab[i];
-    __syncthreads();
-    if (warp == 0) {
-      float t = 0.f;
-      for (int w = 0; w < kLnThreads / 32; ++w) t += red[w][lane];
-      part_b[(int64_t)blockIdx.x * c + lane + 32 * i] = t;
-    }
-    __syncthreads();
+  // block partials, fixed order: every (warp, row-in-warp) slot writes its channel vector, then the first c threads sum
+  const int slots = (kLnThreads / 32) * rpw;
+  float* rg = red;
+  float* rb = red + slots * c;
+  const int slot = warp * rpw + rin;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    *reinterpret_cast<float4*>(rg + slot * c + 4 * (sub + i * L)) = ag[i];
+    *reinterpret_cast<float4*>(rb + slot * c + 4 * (sub + i * L)) = ab[i];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += kLnThreads) {
+    float tg = 0.f, tb = 0.f;
+    for (int sl = 0; sl < slots; ++sl) { tg += rg[sl * c + ch]; tb += rb[sl * c + ch]; }
+    part_g[(int64_t)blockIdx.x * c + ch] = tg;
+    part_b[(int64_t)blockIdx.x * c + ch] = tb;
   }
 }
 
@@ -147,10 +190,12 @@ inline size_t layer_norm_bwd_workspace_bytes(int64_t n, int c) { return (size_t)
 
 inline int launch_layer_norm_fwd(const void* x, int xd, const float* gamma, const float* beta, int64_t n, int c, float eps, void* y,
                                  int yd, float* mean, float* rstd, cudaStream_t stream) {
-  B2PC_CHECK_ARG(c % 32 == 0 && c >= 32 && c <= 32 * kLnMaxPerLane, "layer_norm: channels %d not a multiple of 32 in [32,512]", c);
+  B2PC_CHECK_ARG(c == 32 || c == 64 || c == 128 || c == 256 || c == 512, "layer_norm: channels %d not one of 32/64/128/256/512", c);
   if (n == 0) return B2PC_OK;
   const int blocks = ln_blocks(n);
-  B2PC_LN_DISPATCH(xd, yd, (layer_norm_fwd_kernel<X, Y><<<blocks, kLnThreads, 0, stream>>>((const X*)x, gamma, beta, n, c, eps, (Y*)y, mean, rstd)));
+  if (c <= 128) { B2PC_LN_DISPATCH(xd, yd, (layer_norm_fwd_kernel<X, Y, 1><<<blocks, kLnThreads, 0, stream>>>((const X*)x, gamma, beta, n, c, eps, (Y*)y, mean, rstd))); }
+  else if (c == 256) { B2PC_LN_DISPATCH(xd, yd, (layer_norm_fwd_kernel<X, Y, 2><<<blocks, kLnThreads, 0, stream>>>((const X*)x, gamma, beta, n, c, eps, (Y*)y, mean, rstd))); }
+  else { B2PC_LN_DISPATCH(xd, yd, (layer_norm_fwd_kernel<X, Y, 4><<<blocks, kLnThreads, 0, stream>>>((const X*)x, gamma, beta, n, c, eps, (Y*)y, mean, rstd))); }
   count_launches(1);
   B2PC_CHECK_LAUNCH("layer_norm_fwd");
   return B2PC_OK;
@@ -159,7 +204,7 @@ inline int launch_layer_norm_fwd(const void* x, int xd, const float* gamma, cons
 inline int launch_layer_norm_bwd(const void* dy, int yd, const void* x, int xd, const float* gamma, const float* mean,
                                  const float* rstd, int64_t n, int c, void* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                                  cudaStream_t stream) {
-  B2PC_CHECK_ARG(c % 32 == 0 && c >= 32 && c <= 32 * kLnMaxPerLane, "layer_norm: channels %d not a multiple of 32 in [32,512]", c);
+  B2PC_CHECK_ARG(c == 32 || c == 64 || c == 128 || c == 256 || c == 512, "layer_norm: channels %d not one of 32/64/128/256/512", c);
   if (ws_bytes < layer_norm_bwd_workspace_bytes(n, c)) { set_error("layer_norm_bwd: workspace too small"); return B2PC_ERR_WORKSPACE; }
   const int blocks = ln_blocks(n);
   float* pg = (float*)ws;
@@ -169,7 +214,12 @@ inline int launch_layer_norm_bwd(const void* dy, int yd, const void* x, int xd, 
     if (dbeta) cudaMemsetAsync(dbeta, 0, c * sizeof(float), stream);
     return B2PC_OK;
   }
-  B2PC_LN_DISPATCH(xd, yd, (layer_norm_bwd_kernel<X, Y><<<blocks, kLnThreads, 0, stream>>>((const Y*)dy, (const X*)x, gamma, mean, rstd, n, c, (X*)dx, pg, pb)));
+  const int vv = c <= 128 ? 1 : (c == 256 ? 2 : 4);
+  const int rpw = 32 / (c / (4 * vv));
+  const size_t smem = (size_t)2 * (kLnThreads / 32) * rpw * c * sizeof(float);   // <= 32 KB
+  if (vv == 1) { B2PC_LN_DISPATCH(xd, yd, (layer_norm_bwd_kernel<X, Y, 1><<<blocks, kLnThreads, smem, stream>>>((const Y*)dy, (const X*)x, gamma, mean, rstd, n, c, (X*)dx, pg, pb))); }
+  else if (vv == 2) { B2PC_LN_DISPATCH(xd, yd, (layer_norm_bwd_kernel<X, Y, 2><<<blocks, kLnThreads, smem, stream>>>((const Y*)dy, (const X*)x, gamma, mean, rstd, n, c, (X*)dx, pg, pb))); }
+  else { B2PC_LN_DISPATCH(xd, yd, (layer_norm_bwd_kernel<X, Y, 4><<<blocks, kLnThreads, smem, stream>>>((const Y*)dy, (const X*)x, gamma, mean, rstd, n, c, (X*)dx, pg, pb))); }
   layer_norm_param_reduce_kernel<<<c / 32, 256, 0, stream>>>(pg, pb, blocks, c, dgamma, dbeta);
   count_launches(2);
   B2PC_CHECK_LAUNCH("layer_norm_bwd");

@@ -348,7 +348,7 @@ class LayerNormFn(torch.autograd.Function):
 
 
 def layer_norm_supported(x, c):
-    return x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and c % 32 == 0 and 32 <= c <= 512
+    return x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and c in (32, 64, 128, 256, 512)
 
 
 def layer_norm(x, weight, bias, eps=1e-5, emit_autocast_dtype=False):

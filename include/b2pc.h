@@ -169,6 +169,12 @@ int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype,
                         const float* mean, const float* rstd, int64_t n, int c, void* dx, float* dgamma,
                         float* dbeta, void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
 
+/* out[c] = sum_r x[r, c] in fp32 (bias gradient of the Linear layers of the block, point_transformer_v3m1_base.py:96-97,
+ * 238-240; replaces a tall-matrix torch reduction).  C must be a multiple of 4. */
+size_t b2pc_colsum_workspace_bytes(int64_t n, int c);
+int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* workspace, size_t workspace_bytes,
+                b2pc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,4 +215,11 @@ int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype,
                                (cudaStream_t)stream);
 }
 
+size_t b2pc_colsum_workspace_bytes(int64_t n, int c) { return colsum_workspace_bytes(n, c); }
+
+int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(x && out && workspace, "colsum: null pointer");
+  return launch_colsum(x, dtype, n, c, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

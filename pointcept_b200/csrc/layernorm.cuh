@@ -227,3 +227,77 @@ inline int launch_layer_norm_bwd(const void* dy, int yd, const void* x, int xd, 
 }
 
 }  // namespace b2pc
+
+namespace b2pc {
+// ---- column sum of a tall matrix: out[c] = sum_r x[r, c]  (bias gradients of the linears; fp32 result) ---------------------
+// grid.x covers 256-channel slabs, grid.y row chunks; a block is 64 vector-columns x 4 row lanes, fully coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ x, int64_t n, int c, int64_t rows_per_block, float* __restrict__ partial) {
+  __shared__ float4 red[4][64];
+  const int cvi = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int ch = blockIdx.x * 256 + cvi * 4;
+  const int64_t r_begin = blockIdx.y * rows_per_block;
+  int64_t r_end = r_begin + rows_per_block;
+  if (r_end > n) r_end = n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ch < c) {
+    int64_t r = r_begin + rl;
+    for (; r + 12 < r_end; r += 16) {   // 4 independent loads in flight
+      const float4 a = ld4<T>(x + r * c + ch), b = ld4<T>(x + (r + 4) * c + ch), d = ld4<T>(x + (r + 8) * c + ch),
+                   e = ld4<T>(x + (r + 12) * c + ch);
+      acc.x += (a.x + b.x) + (d.x + e.x); acc.y += (a.y + b.y) + (d.y + e.y);
+      acc.z += (a.z + b.z) + (d.z + e.z); acc.w += (a.w + b.w) + (d.w + e.w);
+    }
+    for (; r < r_end; r += 4) {
+      const float4 a = ld4<T>(x + r * c + ch);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  red[rl][cvi] = acc;
+  __syncthreads();
+  if (rl == 0 && ch < c) {
+    float4 t = red[0][cvi];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { t.x += red[i][cvi].x; t.y += red[i][cvi].y; t.z += red[i][cvi].z; t.w += red[i][cvi].w; }
+    *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.y * c + ch) = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int chunks, int c, float* __restrict__ out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float s = 0.f;
+  for (int b = 0; b < chunks; ++b) s += partial[(int64_t)b * c + ch];
+  out[ch] = s;
+}
+
+inline int colsum_chunks(int64_t n, int c) {
+  const int slabs = (c + 255) / 256;
+  int64_t chunks = (2 * kNumSMs + slabs - 1) / slabs;
+  const int64_t max_chunks = ceil_div(n > 0 ? n : 1, 64);
+  if (chunks > max_chunks) chunks = max_chunks;
+  return (int)(chunks < 1 ? 1 : chunks);
+}
+inline size_t colsum_workspace_bytes(int64_t n, int c) { return (size_t)colsum_chunks(n, c) * c * sizeof(float) + 256; }
+
+inline int launch_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  B2PC_CHECK_ARG(c % 4 == 0 && c > 0, "colsum: channels %d not a multiple of 4", c);
+  if (ws_bytes < colsum_workspace_bytes(n, c)) { set_error("colsum: workspace too small"); return B2PC_ERR_WORKSPACE; }
+  if (n == 0) { cudaMemsetAsync(out, 0, c * sizeof(float), stream); return B2PC_OK; }
+  const int chunks = colsum_chunks(n, c);
+  const int64_t rpb = ceil_div(ceil_div(n, chunks), 4) * 4;
+  dim3 grid((c + 255) / 256, chunks);
+  switch (dtype) {
+    case B2PC_F32: colsum_partial_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, n, c, rpb, (float*)ws); break;
+    case B2PC_F16: colsum_partial_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)x, n, c, rpb, (float*)ws); break;
+    case B2PC_BF16: colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, n, c, rpb, (float*)ws); break;
+    default: set_error("colsum: unknown dtype %d", dtype); return B2PC_ERR_INVALID_ARG;
+  }
+  colsum_final_kernel<<<(c + 255) / 256, 256, 0, stream>>>((const float*)ws, chunks, c, out);
+  count_launches(2);
+  B2PC_CHECK_LAUNCH("colsum");
+  return B2PC_OK;
+}
+}  // namespace b2pc

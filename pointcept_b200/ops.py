@@ -419,3 +419,64 @@ class UnpoolAddFn(torch.autograd.Function):
 
 def unpool_add(parent, child, cluster, order, seg_len):
     return UnpoolAddFn.apply(parent, child, cluster, order, seg_len)
+
+
+# ------------------------------------------------------------------------------------------------
+# glue: Linear with a fused bias-gradient reduction (point features are tall matrices: N >> C)
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def colsum(x):
+    """fp32 column sums of a [N, C] CUDA matrix."""
+    _need_cuda(x)
+    x = x.contiguous()
+    n, c = x.shape
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws = _ws(L.b2pc_colsum_workspace_bytes(n, c), x.device)
+    _lib.check(L.b2pc_colsum(_p(x), _DTYPES[x.dtype], n, c, _p(out), _p(ws), ws.numel(), _stream()), "colsum")
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b in the compute dtype (the autocast dtype under autocast), gradients as autocast produces them, except
+    that the bias gradient is one fused fp32 column-sum kernel instead of a tall-matrix torch reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cdtype):
+        xc = x if x.dtype == cdtype else x.to(cdtype)
+        wc = weight if weight.dtype == cdtype else weight.to(cdtype)
+        bc = None if bias is None else (bias if bias.dtype == cdtype else bias.to(cdtype))
+        with torch.autocast("cuda", enabled=False):
+            y = torch.nn.functional.linear(xc, wc, bc)
+        ctx.save_for_backward(xc, wc)
+        ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc = ctx.saved_tensors
+        xd, wd, bd = ctx.meta
+        dy = dy.contiguous()
+        dx = dw = db = None
+        with torch.autocast("cuda", enabled=False):
+            if ctx.needs_input_grad[0]:
+                dx = dy @ wc
+                if dx.dtype != xd:
+                    dx = dx.to(xd)
+            if ctx.needs_input_grad[1]:
+                dw = dy.t() @ xc
+                if dw.dtype != wd:
+                    dw = dw.to(wd)
+            if bd is not None and ctx.needs_input_grad[2]:
+                db = colsum(dy)
+                if db.dtype != bd:
+                    db = db.to(bd)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias):
+    """F.linear for 2-D CUDA inputs with the fused bias gradient; falls back to F.linear otherwise."""
+    if x.is_cuda and x.dim() == 2 and weight.shape[0] % 4 == 0 and x.dtype in _DTYPES:
+        cdtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        return LinearFn.apply(x, weight, bias, cdtype)
+    return torch.nn.functional.linear(x, weight, bias)

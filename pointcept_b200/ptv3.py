@@ -47,6 +47,13 @@ class FusedLayerNorm(nn.LayerNorm):
         return super().forward(x)
 
 
+class FusedLinear(nn.Linear):
+    """nn.Linear (same parameters) routed through ops.linear: identical math, fused fp32 bias-gradient reduction."""
+
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
 class _SerializedGather(torch.autograd.Function):
     """y = x[order_pad]  (rows into patch order, ptv3m1:188).  Every point sits at exactly one primary padded slot
     (primary_pos) and at most once more as a borrowed filler of its scene's last patch (dup_slots -> dup_points), so the
@@ -98,8 +105,8 @@ class SerializedAttention(PointModule):
         self.scale = qk_scale or (channels // num_heads) ** -0.5
         self.order_index = order_index
         self.patch_size = patch_size
-        self.qkv = nn.Linear(channels, channels * 3, bias=qkv_bias)
-        self.proj = nn.Linear(channels, channels)
+        self.qkv = FusedLinear(channels, channels * 3, bias=qkv_bias)
+        self.proj = FusedLinear(channels, channels)
         self.proj_drop = nn.Dropout(proj_drop)
 
     @torch.no_grad()
@@ -146,9 +153,9 @@ class MLP(nn.Module):
         super().__init__()
         out_channels = out_channels or in_channels
         hidden_channels = hidden_channels or in_channels
-        self.fc1 = nn.Linear(in_channels, hidden_channels)
+        self.fc1 = FusedLinear(in_channels, hidden_channels)
         self.act = act_layer()
-        self.fc2 = nn.Linear(hidden_channels, out_channels)
+        self.fc2 = FusedLinear(hidden_channels, out_channels)
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
@@ -165,7 +172,7 @@ class Block(PointModule):
         self.channels, self.pre_norm = channels, pre_norm
         self.cpe = PointSequential(
             spconv.SubMConv3d(channels, channels, kernel_size=3, bias=True, indice_key=cpe_indice_key),
-            nn.Linear(channels, channels),
+            FusedLinear(channels, channels),
             norm_layer(channels),
         )
         self.norm1 = PointSequential(norm_layer(channels))
@@ -216,7 +223,7 @@ class SerializedPooling(PointModule):
         self.stride = stride
         assert reduce in ["sum", "mean", "min", "max"]
         self.reduce, self.shuffle_orders, self.traceable = reduce, shuffle_orders, traceable
-        self.proj = nn.Linear(in_channels, out_channels)
+        self.proj = FusedLinear(in_channels, out_channels)
         if norm_layer is not None:
             self.norm = PointSequential(norm_layer(out_channels))
         if act_layer is not None:
@@ -306,8 +313,8 @@ class SerializedUnpooling(PointModule):
 
     def __init__(self, in_channels, skip_channels, out_channels, norm_layer=None, act_layer=None, traceable=False):
         super().__init__()
-        self.proj = PointSequential(nn.Linear(in_channels, out_channels))
-        self.proj_skip = PointSequential(nn.Linear(skip_channels, out_channels))
+        self.proj = PointSequential(FusedLinear(in_channels, out_channels))
+        self.proj_skip = PointSequential(FusedLinear(skip_channels, out_channels))
         if norm_layer is not None:
             self.proj.add(norm_layer(out_channels))
             self.proj_skip.add(norm_layer(out_channels))

@@ -430,3 +430,25 @@ def test_segment_max_and_unpool_add_vs_plain_torch(dtype):
     (p2 + c2[cluster]).backward(dy.double().cpu())
     assert rel_l2(pg.grad.float(), p2.grad) < 1e-6
     assert rel_l2(cg.grad.float(), c2.grad) < (1e-6 if dtype == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 96), (64, 64), (128, 512), (64, 20), (512, 1536)])
+@pytest.mark.parametrize("autocast", [False, True])
+def test_fused_linear_matches_torch_linear(cin, cout, autocast):
+    torch.manual_seed(0)
+    n = 4099
+    x = torch.randn(n, cin, device=DEV, requires_grad=True)
+    w = (torch.randn(cout, cin, device=DEV) * 0.1).requires_grad_(True)
+    b = torch.randn(cout, device=DEV).requires_grad_(True)
+    x2, w2, b2 = [t.detach().clone().requires_grad_(True) for t in (x, w, b)]
+    dy = torch.randn(n, cout, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        y = ops.linear(x, w, b)
+        y2 = torch.nn.functional.linear(x2, w2, b2)
+    assert y.dtype == y2.dtype and torch.equal(y, y2)
+    y.backward(dy.to(y.dtype))
+    y2.backward(dy.to(y2.dtype))
+    assert torch.equal(x.grad, x2.grad) and torch.equal(w.grad, w2.grad)
+    # bias gradient: ours is an fp32 sum of the (bf16) upstream gradient, torch's is a bf16-accumulated reduction under autocast
+    assert rel_l2(b.grad, dy.to(y.dtype).double().sum(0)) < 1e-5
+    assert rel_l2(b.grad, b2.grad) < (1e-5 if not autocast else 1e-2)

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-voxels", type=int, default=120_000, help="scene size of the bounded CPU sample (one scene)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-timeout", type=int, default=240)
+    ap.add_argument("--fused-linear", action="store_true", help="fused bias-gradient Linear (pays off for GPU-bound batches)")
     ap.add_argument("--no-reorder", action="store_true", help="keep level-0 points in input order (no z-order memory layout)")
     ap.add_argument("--kernel-impl", type=int, default=None, help="0 auto, 1 SIMT kernels, 2 tcgen05 kernels")
     return ap.parse_args()
@@ -208,6 +209,9 @@ def run_ours(args):
     if args.kernel_impl is not None:
         ops.set_impl(args.kernel_impl)
 
+    if args.fused_linear:
+        from pointcept_b200.ptv3 import FusedLinear
+        FusedLinear.use_fused_bias_grad = True
     torch.manual_seed(0)
     model = PTv3Segmentor(num_classes=20, backbone_out_channels=64, spatial_reorder=not args.no_reorder,
                           **ptv3_base_config()).to(dev).train()

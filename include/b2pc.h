@@ -133,9 +133,11 @@ int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* s
  *                 k -> KV-1-k), strided / inverse convs pass the opposite-direction table.
  * n_in rows of feat, n_out rows of out / columns of pair.  impl as for attention.
  * ------------------------------------------------------------------------------------------- */
+size_t b2pc_spconv_gather_gemm_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv);
 int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bias, const int32_t* pair,
                             int64_t pair_stride, int64_t n_in, int64_t n_out, int c_in, int c_out, int kv,
-                            int transpose_w, int flip, int dtype, void* out, int impl, b2pc_stream_t stream);
+                            int transpose_w, int flip, int dtype, void* out, void* workspace,
+                            size_t workspace_bytes, int impl, b2pc_stream_t stream);
 
 size_t b2pc_spconv_bwd_weight_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv);
 /* dweight[co, k, ci] = sum_j  dout[j, co] * feat_in[pair[k, j], ci]   (fp32 result, deterministic). */

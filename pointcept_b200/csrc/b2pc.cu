@@ -128,15 +128,27 @@ int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* s
 }
 
 // ---- sparse convolution arithmetic ---------------------------------------------------------------------
+size_t b2pc_spconv_gather_gemm_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
+#ifndef B2PC_NO_UMMA
+  return conv_umma_workspace_bytes(n_out, c_in, c_out, kv);
+#else
+  return 0;
+#endif
+}
+
 int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bias, const int32_t* pair, int64_t pair_stride,
                             int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, int dtype,
-                            void* out, int impl, b2pc_stream_t stream) {
+                            void* out, void* workspace, size_t workspace_bytes, int impl, b2pc_stream_t stream) {
   B2PC_CHECK_ARG(feat && weight && pair && out, "spconv_gather_gemm: null pointer");
   B2PC_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && kv > 0 && pair_stride >= n_out, "spconv_gather_gemm: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
 #ifndef B2PC_NO_UMMA
   if (impl != 1) {
-    if (spconv_umma_supported(dtype, c_in, c_out)) return launch_gather_gemm_umma(feat, weight, bias, pair, pair_stride, n_in, n_out, c_in, c_out, kv, transpose_w, flip, dtype, out, s);
+    if (spconv_umma_supported(dtype, c_in, c_out)) {
+      const size_t need = conv_umma_workspace_bytes(n_out, c_in, c_out, kv);
+      if (need > 0 && (!workspace || workspace_bytes < need)) { set_error("spconv_gather_gemm: workspace too small"); return B2PC_ERR_WORKSPACE; }
+      return launch_gather_gemm_umma(feat, weight, bias, pair, pair_stride, n_in, n_out, c_in, c_out, kv, transpose_w, flip, dtype, out, workspace, s);
+    }
     if (impl == 2) { set_error("spconv_gather_gemm: tcgen05 kernel does not support dtype %d c_in %d c_out %d", dtype, c_in, c_out); return B2PC_ERR_UNSUPPORTED; }
   }
 #else

@@ -8,7 +8,8 @@
 // cp.async, the matching W_k slice is staged next to it, and one thread issues KC/16 tcgen05.mma (M=128, N=n_tile,
 // K=16).  Offsets with no partner in the whole tile are skipped.  A ring of stages keeps several gathers in flight
 // while the tensor core drains earlier ones; stage reuse is gated by tcgen05.commit -> mbarrier.
-// No atomics: every output element is written once, deterministically.
+// Every output element is written once (deterministic) unless the launch is under-filled, in which case the offsets are
+// split over several CTAs per tile that add fp32 partials with red.global.add (order-dependent in the last fp32 bits).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -20,19 +21,25 @@ constexpr int kCuM = 128;       // output rows per CTA (= threads)
 constexpr int kCuMaxKV = 32;    // kernel volume limit of this path (27 for 3^3, 8 for 2^3)
 constexpr int kCuMaxStages = 4;   // ring depth (prefetch distance 2)
 
-struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes, idx_rows, grp; };
+struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes, idx_rows, grp, ksplit; };
 
 inline ConvUmmaCfg conv_umma_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   ConvUmmaCfg c;
   c.kc = c_in % 64 == 0 ? 64 : (c_in % 32 == 0 ? 32 : 16);
-  // widest N tile (fewest re-gathers of A) that still yields ~100 CTAs; never narrower than 64 columns
+  // widest legal N tile (A rows are gathered once per N tile); when that leaves the GPU under-filled (deep, narrow-N
+  // levels: a few dozen row tiles, 27 offsets x C/64 chunks of strictly sequential work each) the kernel offsets are split
+  // over `ksplit` CTAs per tile, which add their partial sums into an fp32 scratch with vector reductions
   const int64_t m_tiles = ceil_div(n_out > 0 ? n_out : 1, kCuM);
-  c.n_tile = 0;
-  for (int nt = c_out <= 256 ? c_out : 256; nt >= 16; nt -= 16) {
-    if (c_out % nt != 0) continue;
-    if (c.n_tile == 0) c.n_tile = nt;                 // widest legal tile
-    if (m_tiles * (c_out / nt) >= 100 || nt <= 64) { c.n_tile = nt; break; }
-    c.n_tile = nt;
+  c.n_tile = 16;
+  for (int nt = c_out <= 256 ? c_out : 256; nt >= 16; nt -= 16)
+    if (c_out % nt == 0) { c.n_tile = nt; break; }
+  const int64_t ctas = m_tiles * (c_out / c.n_tile);
+  c.ksplit = 1;
+  if (ctas < 100 && kv > 1) {
+    int64_t ks = ceil_div(2 * kNumSMs, ctas);
+    if (ks > 9) ks = 9;
+    if (ks > kv) ks = kv;
+    c.ksplit = (int)ks;
   }
   c.tmem_cols = 32;
   while (c.tmem_cols < c.n_tile) c.tmem_cols <<= 1;
@@ -62,7 +69,8 @@ template <typename T>
 __global__ void __launch_bounds__(kCuM)
 gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                         const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
-                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols, int idx_rows, int grp) {
+                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols, int idx_rows, int grp,
+                        int ksplit, float* __restrict__ acc) {
   using namespace umma;
   extern __shared__ __align__(128) uint8_t smem[];
   int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                       // [idx_rows][128]
@@ -121,7 +129,13 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
       if (lane == 0 && wmask) atomicOr(mask_s, wmask);
     }
     __syncthreads();
-    const uint32_t mask = *mask_s;
+    uint32_t mask = *mask_s;
+    if (ksplit > 1) {   // this CTA's share of the offsets: k % ksplit == blockIdx.z
+      uint32_t mine = 0;
+      for (int k = 0; k < kcnt; ++k)
+        if ((kb + k) % ksplit == (int)blockIdx.z) mine |= 1u << k;
+      mask &= mine;
+    }
     const int n_act = __popc(mask);
     const int n_units = n_act * n_cc;             // unit = (active offset, channel chunk)
     const int n_it = (n_units + grp - 1) / grp;   // an iteration (= pipeline stage) carries up to grp units
@@ -207,7 +221,15 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
 #pragma unroll
       for (int i = 0; i < 16; ++i) r[i] = 0;
     }
-    if (j < n_out) {
+    if (ksplit > 1) {
+      if (j < n_out && n_it > 0) {
+        float* dst = acc + j * c_out + n0 + cb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          red_add_v4(dst + 4 * i, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                     __uint_as_float(r[4 * i + 3]));
+      }
+    } else if (j < n_out) {
       uint32_t w[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -225,20 +247,49 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// out[j, c] = acc[j, c] + bias[c]   (offset-split path)
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_split_finish_kernel(const float* __restrict__ acc, const T* __restrict__ bias, int64_t n_out, int c_out, T* __restrict__ out) {
+  const int64_t total = n_out * c_out / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(acc)[i];
+    const int c0 = (int)((i * 4) % c_out);
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    if (bias) { b0 = to_f32(bias[c0]); b1 = to_f32(bias[c0 + 1]); b2 = to_f32(bias[c0 + 2]); b3 = to_f32(bias[c0 + 3]); }
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack2<T>(v.x + b0, v.y + b1), pack2<T>(v.z + b2, v.w + b3));
+  }
+}
+
+inline size_t conv_umma_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
+  if (c_in % 16 != 0 || c_out % 16 != 0) return 0;
+  const ConvUmmaCfg c = conv_umma_cfg(n_out, c_in, c_out, kv);
+  return c.ksplit > 1 ? (size_t)n_out * c_out * sizeof(float) + 256 : 0;
+}
+
 template <typename T>
 inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const void* bias, const int32_t* pair,
                                      int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip,
-                                     void* out, cudaStream_t stream) {
+                                     void* out, void* ws, cudaStream_t stream) {
   const ConvUmmaCfg c = conv_umma_cfg(n_out, c_in, c_out, kv);
   static int max_smem_set = 0;
   if (c.smem_bytes > max_smem_set) {
     cudaFuncSetAttribute(gather_gemm_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
     max_smem_set = c.smem_bytes;
   }
-  dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile);
+  dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile, c.ksplit);
+  float* acc = (float*)ws;
+  if (c.ksplit > 1) cudaMemsetAsync(acc, 0, (size_t)n_out * c_out * sizeof(float), stream);
   gather_gemm_umma_kernel<T><<<grid, kCuM, c.smem_bytes, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair,
                                                                    pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,
-                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows, c.grp);
+                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows, c.grp, c.ksplit,
+                                                                   acc);
+  if (c.ksplit > 1) {
+    int64_t fb = ceil_div(n_out * c_out / 4, 256);
+    if (fb > kNumSMs * 8) fb = kNumSMs * 8;
+    conv_split_finish_kernel<T><<<(int)fb, 256, 0, stream>>>(acc, (const T*)bias, n_out, c_out, (T*)out);
+    count_launches(1);
+  }
   count_launches(1);
   B2PC_CHECK_LAUNCH("spconv_gather_gemm(tcgen05)");
   return B2PC_OK;
@@ -246,12 +297,12 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
 
 inline int launch_gather_gemm_umma(const void* feat, const void* weight, const void* bias, const int32_t* pair, int64_t pair_stride,
                                    int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, int dtype,
-                                   void* out, cudaStream_t stream) {
+                                   void* out, void* ws, cudaStream_t stream) {
   (void)n_in;
   if (n_out == 0) return B2PC_OK;
   if (dtype == B2PC_BF16)
-    return launch_gather_gemm_umma_t<__nv_bfloat16>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream);
-  return launch_gather_gemm_umma_t<__half>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream);
+    return launch_gather_gemm_umma_t<__nv_bfloat16>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, ws, stream);
+  return launch_gather_gemm_umma_t<__half>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, ws, stream);
 }
 
 }  // namespace b2pc

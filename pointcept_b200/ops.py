@@ -244,10 +244,12 @@ def rulebook_strided(indices, spatial_shape, ksize, stride, padding=0, dilation=
 def _gather_gemm(feat, weight, bias, pair, n_out, c_in, c_out, kv, transpose_w, flip):
     out = torch.empty((n_out, c_out), dtype=feat.dtype, device=feat.device)
     L = _lib.lib()
+    wsb = L.b2pc_spconv_gather_gemm_workspace_bytes(n_out, c_in, c_out, kv)
+    ws = _ws(wsb, feat.device) if wsb else None
     with _timed("spconv_gather_gemm", (pair, c_in, c_out, feat.element_size())):
         _lib.check(L.b2pc_spconv_gather_gemm(_p(feat), _p(weight), _p(bias), _p(pair), pair.shape[1], feat.shape[0], n_out, c_in,
-                                             c_out, kv, int(transpose_w), int(flip), _DTYPES[feat.dtype], _p(out), _impl, _stream()),
-                   "spconv_gather_gemm")
+                                             c_out, kv, int(transpose_w), int(flip), _DTYPES[feat.dtype], _p(out), _p(ws), wsb, _impl,
+                                             _stream()), "spconv_gather_gemm")
     return out
 
 

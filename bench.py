@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "points/sec fwd+bwd (PTv3-base, ScanNet-scale synth)"
+METRIC = "points/sec fwd+bwd (PTv3-base, ScanNet-scale synth)"   # --workload spunet34 reports the same unit for SpUNet-34
 UNIT = "points/s"
 
 
@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--cpu-voxels", type=int, default=120_000, help="scene size of the bounded CPU sample (one scene)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-timeout", type=int, default=240)
+    ap.add_argument("--workload", default="ptv3_base", choices=["ptv3_base", "spunet34"],
+                    help="ptv3_base = the headline metric (BASELINE config 4 shape); spunet34 = BASELINE config 3 (supplementary)")
     ap.add_argument("--fused-linear", action="store_true", help="fused bias-gradient Linear (pays off for GPU-bound batches)")
     ap.add_argument("--no-reorder", action="store_true", help="keep level-0 points in input order (no z-order memory layout)")
     ap.add_argument("--kernel-impl", type=int, default=None, help="0 auto, 1 SIMT kernels, 2 tcgen05 kernels")
@@ -213,8 +215,27 @@ def run_ours(args):
         from pointcept_b200.ptv3 import FusedLinear
         FusedLinear.use_fused_bias_grad = True
     torch.manual_seed(0)
-    model = PTv3Segmentor(num_classes=20, backbone_out_channels=64, spatial_reorder=not args.no_reorder,
-                          **ptv3_base_config()).to(dev).train()
+    if args.workload == "spunet34":
+        from pointcept_b200.spunet import SpUNetBase
+
+        class _SpUNetSeg(torch.nn.Module):
+            """SpUNet-v1m1 stock widths (configs/scannet/semseg-spunet-v1m1-0-base.py:10-20) + CE loss"""
+
+            def __init__(self):
+                super().__init__()
+                self.backbone = SpUNetBase(6, 20)
+
+            def prepare(self, d):
+                return d
+
+            def forward(self, d):
+                logits = self.backbone(d)
+                return dict(seg_logits=logits, loss=torch.nn.functional.cross_entropy(logits.float(), d["segment"]))
+
+        model = _SpUNetSeg().to(dev).train()
+    else:
+        model = PTv3Segmentor(num_classes=20, backbone_out_channels=64, spatial_reorder=not args.no_reorder,
+                              **ptv3_base_config()).to(dev).train()
     n_params = sum(p.numel() for p in model.parameters())
     net = model
     if world > 1:
@@ -255,7 +276,12 @@ def run_ours(args):
             point["segment"] = d["segment"]
             ev = torch.cuda.Event()
             ev.record(side)
-        point.record_stream(main)
+        if hasattr(point, "record_stream"):
+            point.record_stream(main)
+        else:
+            for v in point.values():
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(main)
         return point, ev
 
     def run_steps(n, make_inputs, on_loss=None):
@@ -388,8 +414,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "PT-v3m1 base (configs/scannet/semseg-pt-v3m1-0-base.py) fwd+bwd+AdamW, BASELINE config 4 shape: "
-                               f"{args.scenes_per_gpu} synthetic ScanNet-scale scenes per GPU",
+        "config": {"workload": ("PT-v3m1 base (configs/scannet/semseg-pt-v3m1-0-base.py) fwd+bwd+AdamW, BASELINE config 4 shape: "
+                                if args.workload == "ptv3_base" else
+                                "SpUNet-v1m1 34 (configs/scannet/semseg-spunet-v1m1-0-base.py) fwd+bwd+AdamW, BASELINE config 3 shape: ")
+                               + f"{args.scenes_per_gpu} synthetic ScanNet-scale scenes per GPU",
                    "scenes_per_gpu": args.scenes_per_gpu, "points_per_gpu": n_points, "global_points": int(total_points),
                    "params_M": round(n_params / 1e6, 2), "patch_size": 1024, "orders": 4, "parallelism": f"dp{world}",
                    "l2": "no explicit flush: one step streams several GB of activations, far beyond the 126 MB L2",

@@ -36,12 +36,14 @@ constexpr int kAuQ = 128;      // queries per CTA
 constexpr int kAuStages = 3;   // K/V ring depth
 
 template <int BN> __host__ __device__ constexpr int attn_tmem_cols() { return BN == 128 ? 256 : 128; }
-template <int BN> __host__ __device__ constexpr int attn_fwd_smem_bytes() { return kAuQ * 32 + kAuStages * BN * 64 + 64; }
+template <int BN> __host__ __device__ constexpr int attn_fwd_smem_bytes() { return kAuQ * 32 + kAuStages * BN * 64 + 128; }
 
-template <typename T, int BN>
+// TMA = true: Q / K / V tiles arrive by cp.async.bulk.tensor (one elected thread, byte-counted mbarriers); false: cp.async.
+template <typename T, int BN, bool TMA>
 __global__ void __launch_bounds__(kAuQ)
 attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, int64_t t_total, int H, float scale,
-                     T* __restrict__ out, float* __restrict__ lse, AttnDesc dd) {
+                     T* __restrict__ out, float* __restrict__ lse, AttnDesc dd, const __grid_constant__ CUtensorMap tmap_q,
+                     const __grid_constant__ CUtensorMap tmap_kv) {
   using namespace umma;
   constexpr int D = 16;
   constexpr int TMEM_COLS = attn_tmem_cols<BN>();
@@ -50,7 +52,9 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
   uint8_t* q_s = smem;
   uint8_t* kv_s = smem + kAuQ * 32;
   uint64_t* bar = reinterpret_cast<uint64_t*>(kv_s + kAuStages * BN * 64);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* full = bar + 1;             // [kAuStages] K/V stage landed (TMA path)
+  uint64_t* qbar = full + kAuStages;    // Q tile landed (TMA path)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int seq = blockIdx.y, h = blockIdx.z;
@@ -62,13 +66,37 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
   const int64_t row_stride = (int64_t)3 * H * D;  // elements between consecutive tokens
 
   if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    for (int s = 0; s < kAuStages; ++s) mbar_init(&full[s], 1);
+    mbar_init(qbar, 1);
+    fence_mbar_init();
+  }
+  // TMA: rows past the end of the sequence are whatever follows in the packed tensor (or zeros past T); they only ever
+  // meet masked score columns / zero probabilities, exactly like the zero-filled rows of the cp.async path.
+  auto tma_kv = [&](int blk, int stage) {
+    uint8_t* ks = kv_s + stage * BN * 64;
+    const int row = (int)(s0 + blk * BN);
+    mbar_expect_tx(&full[stage], BN * 64);
+    tma_load_2d(smem_u32(ks), &tmap_kv, (1 * H + h) * D, row, &full[stage]);
+    tma_load_2d(smem_u32(ks + BN * 16), &tmap_kv, (1 * H + h) * D + 8, row, &full[stage]);
+    tma_load_2d(smem_u32(ks + BN * 32), &tmap_kv, (2 * H + h) * D, row, &full[stage]);
+    tma_load_2d(smem_u32(ks + BN * 48), &tmap_kv, (2 * H + h) * D + 8, row, &full[stage]);
+  };
 
   // ---- loads: 16-byte pieces into "plane" layout: piece (row r, chunk c) -> c * rows*16 + r*16 ----------------------
   const T* base_q = qkv + (s0 * 3 + 0) * H * D + h * D;
   const T* base_k = qkv + (s0 * 3 + 1) * H * D + h * D;
   const T* base_v = qkv + (s0 * 3 + 2) * H * D + h * D;
-  {
+  if (TMA) {
+    if (tid == 0) {
+      mbar_expect_tx(qbar, kAuQ * 32);
+      tma_load_2d(smem_u32(q_s), &tmap_q, h * D, (int)(s0 + q0), qbar);
+      tma_load_2d(smem_u32(q_s + kAuQ * 16), &tmap_q, h * D + 8, (int)(s0 + q0), qbar);
+      tma_kv(0, 0);
+      if (nblk > 1) tma_kv(1, 1);
+    }
+  } else {
     const int r = tid;
     const bool ok = q0 + r < len;
     const T* src = base_q + (int64_t)(q0 + r) * row_stride;
@@ -86,10 +114,12 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
       cp_async16(smem_u32((which ? vs : ks) + c * BN * 16 + r * 16), ok ? src : base_k, ok);
     }
   };
-  load_kv(0, 0);
-  cp_async_commit();
-  if (nblk > 1) load_kv(1, 1);
-  cp_async_commit();
+  if (!TMA) {
+    load_kv(0, 0);
+    cp_async_commit();
+    if (nblk > 1) load_kv(1, 1);
+    cp_async_commit();
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -110,10 +140,16 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     const int stage = j % kAuStages;
     uint8_t* ks = kv_s + stage * BN * 64;
     uint8_t* vs = ks + BN * 32;
-    cp_async_wait<1>();
-    fence_proxy_async();
-    __syncthreads();
+    if (!TMA) {
+      cp_async_wait<1>();
+      fence_proxy_async();
+      __syncthreads();
+    }
     if (tid == 0) {
+      if (TMA) {
+        if (j == 0) mbar_wait(qbar, 0);
+        mbar_wait(&full[stage], (j / kAuStages) & 1);
+      }
       tc_fence_after();
       mma_ss(tmem_base + COL_S, desc_q, make_smem_desc(smem_u32(ks), dd.k_lbo, dd.k_sbo), idesc_s, 0);
       mma_commit(bar);
@@ -121,8 +157,12 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     mbar_wait(bar, j & 1);
     tc_fence_after();
     // S_j is complete, hence so is PV_{j-1}: its K/V stage is free again -> prefetch block j+2 into it
-    if (j + 2 < nblk) load_kv(j + 2, (j + 2) % kAuStages);
-    cp_async_commit();
+    if (TMA) {
+      if (tid == 0 && j + 2 < nblk) tma_kv(j + 2, (j + 2) % kAuStages);
+    } else {
+      if (j + 2 < nblk) load_kv(j + 2, (j + 2) % kAuStages);
+      cp_async_commit();
+    }
     if (j > 0) {
       uint32_t r[16];
       tmem_ld16(lane_base + COL_O, r);
@@ -249,17 +289,30 @@ inline AttnDesc attn_desc(int bn) {
   return d;
 }
 
+inline bool attn_use_tma() {
+  static bool v = [] { const char* e = getenv("B2PC_ATTN_TMA"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+
 template <typename T, int BN>
 inline int launch_attn_fwd_umma_t(const void* qkv, const int32_t* cu, int n_seq, int max_seqlen, int64_t t, int H, float scale,
                                   void* out, float* lse, cudaStream_t stream) {
   static bool configured = false;
   constexpr int smem = attn_fwd_smem_bytes<BN>();
   if (!configured) {
-    cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(max_seqlen, kAuQ), n_seq, H);
-  attn_fwd_umma_kernel<T, BN><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN));
+  CUtensorMap mq, mkv;
+  const bool bf16 = UmmaFmt<T>::v == umma::kFmtBF16;
+  const bool tma = attn_use_tma() && t < (1ll << 31) && make_plane_tensor_map(&mq, qkv, bf16, (uint64_t)t, (uint64_t)3 * H * 16, kAuQ) &&
+                   make_plane_tensor_map(&mkv, qkv, bf16, (uint64_t)t, (uint64_t)3 * H * 16, BN);
+  if (tma)
+    attn_fwd_umma_kernel<T, BN, true><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN), mq, mkv);
+  else
+    attn_fwd_umma_kernel<T, BN, false><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN), mq, mkv);
   count_launches(1);
   B2PC_CHECK_LAUNCH("patch_attn_fwd(tcgen05)");
   return B2PC_OK;

@@ -239,7 +239,8 @@ def run_ours(args):
     n_params = sum(p.numel() for p in model.parameters())
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
+                                                        gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
 
     # synthetic batch of this rank (weak scaling: per-GPU work fixed), resident in pinned host memory

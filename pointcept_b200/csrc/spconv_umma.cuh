@@ -65,13 +65,17 @@ inline bool spconv_umma_supported(int dtype, int c_in, int c_out) {
   return true;
 }
 
-template <typename T>
+// KC_T / NT_T: compile-time channel chunk and N tile for the common layer widths (0 = use the runtime arguments); the
+// specialisations let the compiler fold the address arithmetic of the staging loops, which otherwise dominates the issue slots.
+template <typename T, int KC_T, int NT_T>
 __global__ void __launch_bounds__(kCuM)
 gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                         const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
-                        int transpose_w, int flip, T* __restrict__ out, int kc, int n_tile, int stages, int tmem_cols, int idx_rows, int grp,
-                        int ksplit, float* __restrict__ acc) {
+                        int transpose_w, int flip, T* __restrict__ out, int kc_arg, int n_tile_arg, int stages, int tmem_cols, int idx_rows,
+                        int grp, int ksplit, float* __restrict__ acc) {
   using namespace umma;
+  const int kc = KC_T ? KC_T : kc_arg;
+  const int n_tile = NT_T ? NT_T : n_tile_arg;
   extern __shared__ __align__(128) uint8_t smem[];
   int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                       // [idx_rows][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + idx_rows * kCuM * 4);  // [kCuMaxStages]
@@ -272,18 +276,27 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
                                      int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip,
                                      void* out, void* ws, cudaStream_t stream) {
   const ConvUmmaCfg c = conv_umma_cfg(n_out, c_in, c_out, kv);
-  static int max_smem_set = 0;
-  if (c.smem_bytes > max_smem_set) {
-    cudaFuncSetAttribute(gather_gemm_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
-    max_smem_set = c.smem_bytes;
-  }
   dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile, c.ksplit);
   float* acc = (float*)ws;
   if (c.ksplit > 1) cudaMemsetAsync(acc, 0, (size_t)n_out * c_out * sizeof(float), stream);
-  gather_gemm_umma_kernel<T><<<grid, kCuM, c.smem_bytes, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair,
-                                                                   pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,
-                                                                   c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows, c.grp, c.ksplit,
-                                                                   acc);
+#define B2PC_CONV_LAUNCH(KC, NT)                                                                                                   \
+  do {                                                                                                                             \
+    static int max_smem_set = 0;                                                                                                   \
+    if (c.smem_bytes > max_smem_set) {                                                                                             \
+      cudaFuncSetAttribute(gather_gemm_umma_kernel<T, KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);         \
+      max_smem_set = c.smem_bytes;                                                                                                 \
+    }                                                                                                                              \
+    gather_gemm_umma_kernel<T, KC, NT><<<grid, kCuM, c.smem_bytes, stream>>>(                                                      \
+        (const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,   \
+        c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows, c.grp, c.ksplit, acc);                                                  \
+  } while (0)
+  if (c.kc == 32 && c.n_tile == 32) B2PC_CONV_LAUNCH(32, 32);
+  else if (c.kc == 64 && c.n_tile == 64) B2PC_CONV_LAUNCH(64, 64);
+  else if (c.kc == 64 && c.n_tile == 128) B2PC_CONV_LAUNCH(64, 128);
+  else if (c.kc == 64 && c.n_tile == 256) B2PC_CONV_LAUNCH(64, 256);
+  else if (c.kc == 16 && c.n_tile == 32) B2PC_CONV_LAUNCH(16, 32);
+  else B2PC_CONV_LAUNCH(0, 0);
+#undef B2PC_CONV_LAUNCH
   if (c.ksplit > 1) {
     int64_t fb = ceil_div(n_out * c_out / 4, 256);
     if (fb > kNumSMs * 8) fb = kNumSMs * 8;

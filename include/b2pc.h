@@ -171,6 +171,13 @@ int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype,
                         const float* mean, const float* rstd, int64_t n, int c, void* dx, float* dgamma,
                         float* dbeta, void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
 
+/* Stochastic depth fused with the residual add (point_transformer_v3m1_base.py:313-334: shortcut + drop_path(x)):
+ * out[r, :] = shortcut[r, :] + x[r, :] * rowscale[r]  (out has shortcut's dtype); backward dx[r, :] = dy[r, :] * rowscale[r]. */
+int b2pc_rowscale_add(const void* shortcut, int s_dtype, const void* x, int x_dtype, const float* rowscale, int64_t n,
+                      int c, void* out, b2pc_stream_t stream);
+int b2pc_rowscale(const void* dy, int s_dtype, const float* rowscale, int64_t n, int c, void* dx, int x_dtype,
+                  b2pc_stream_t stream);
+
 /* out[c] = sum_r x[r, c] in fp32 (bias gradient of the Linear layers of the block, point_transformer_v3m1_base.py:96-97,
  * 238-240; replaces a tall-matrix torch reduction).  C must be a multiple of 4. */
 size_t b2pc_colsum_workspace_bytes(int64_t n, int c);

@@ -9,7 +9,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2pc.so")
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-Xlinker", "-soname=libb2pc.so"]
+BINDING_DIR = os.path.join(_HERE, "_build_torch_binding")
+BINDING_PATH = os.path.join(BINDING_DIR, "_b2pc_torch.so")
 
 _lib = None
 
@@ -61,6 +63,10 @@ _SIGS = {
     "b2pc_layer_norm_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "b2pc_rowscale_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "b2pc_rowscale": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_int, ctypes.c_void_p]),
     "b2pc_colsum_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
     "b2pc_colsum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_size_t, ctypes.c_void_p]),
@@ -80,6 +86,37 @@ def build(verbose=False, extra_flags=()):
     return LIB_PATH
 
 
+def build_torch_binding(verbose=False):
+    """Compile the pybind/C++ autograd binding (csrc/torch_binding.cpp) in-tree against this torch; g++ only, no GPU needed."""
+    from torch.utils import cpp_extension
+    os.makedirs(BINDING_DIR, exist_ok=True)
+    lib()  # libb2pc.so must be loaded (by soname) before the module that depends on it is imported
+    return cpp_extension.load(name="_b2pc_torch", sources=[os.path.join(CSRC, "torch_binding.cpp")], build_directory=BINDING_DIR,
+                              extra_cflags=["-O2", "-std=c++17"],
+                              extra_ldflags=[f"-L{_HERE}", "-lb2pc"], with_cuda=True,
+                              verbose=verbose)
+
+
+_binding = None
+
+
+def torch_binding():
+    """The compiled binding if it has been built (and B2PC_BINDING != ctypes), else None: ops.py then uses the ctypes path.
+    Both bindings call the same C ABI; neither is a CPU fallback."""
+    global _binding
+    if _binding is None:
+        _binding = False
+        if os.environ.get("B2PC_BINDING", "") != "ctypes" and os.path.exists(BINDING_PATH):
+            import importlib.util
+            import torch  # noqa: F401  (libtorch symbols)
+            lib()
+            spec = importlib.util.spec_from_file_location("_b2pc_torch", BINDING_PATH)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _binding = mod
+    return _binding or None
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True
@@ -95,7 +132,7 @@ def lib():
             raise RuntimeError(
                 f"pointcept_b200: {LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU or PyTorch fallback for these operators.")
-        l = ctypes.CDLL(LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)  # raises AttributeError if the symbol is missing
             fn.restype = res

@@ -227,6 +227,17 @@ int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype,
                                (cudaStream_t)stream);
 }
 
+int b2pc_rowscale_add(const void* shortcut, int s_dtype, const void* x, int x_dtype, const float* rowscale, int64_t n, int c, void* out,
+                      b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(shortcut && x && rowscale && out, "rowscale_add: null pointer");
+  return launch_rowscale_add(shortcut, s_dtype, x, x_dtype, rowscale, n, c, out, (cudaStream_t)stream);
+}
+
+int b2pc_rowscale(const void* dy, int s_dtype, const float* rowscale, int64_t n, int c, void* dx, int x_dtype, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(dy && rowscale && dx, "rowscale: null pointer");
+  return launch_rowscale(dy, s_dtype, rowscale, n, c, dx, x_dtype, (cudaStream_t)stream);
+}
+
 size_t b2pc_colsum_workspace_bytes(int64_t n, int c) { return colsum_workspace_bytes(n, c); }
 
 int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {

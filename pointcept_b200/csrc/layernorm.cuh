@@ -301,3 +301,60 @@ inline int launch_colsum(const void* x, int dtype, int64_t n, int c, float* out,
   return B2PC_OK;
 }
 }  // namespace b2pc
+
+namespace b2pc {
+// ---- per-row scaling fused with the residual add (stochastic depth: out = shortcut + x * rowscale[row]) -------------------------
+template <typename S, typename X>
+__global__ void __launch_bounds__(256)
+rowscale_add_kernel(const S* __restrict__ shortcut, const X* __restrict__ x, const float* __restrict__ rowscale, int64_t n, int c,
+                    S* __restrict__ out) {
+  const int64_t total = n * c / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = rowscale[(i * 4) / c];
+    const float4 a = ld4<S>(shortcut + i * 4), b = ld4<X>(x + i * 4);
+    st4<S>(out + i * 4, make_float4(fmaf(b.x, s, a.x), fmaf(b.y, s, a.y), fmaf(b.z, s, a.z), fmaf(b.w, s, a.w)));
+  }
+}
+// dx = dy * rowscale[row]
+template <typename Y, typename X>
+__global__ void __launch_bounds__(256)
+rowscale_kernel(const Y* __restrict__ dy, const float* __restrict__ rowscale, int64_t n, int c, X* __restrict__ dx) {
+  const int64_t total = n * c / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = rowscale[(i * 4) / c];
+    const float4 a = ld4<Y>(dy + i * 4);
+    st4<X>(dx + i * 4, make_float4(a.x * s, a.y * s, a.z * s, a.w * s));
+  }
+}
+
+#define B2PC_RS_DISPATCH(SD, XD, CALL)                                                              \
+  if (SD == B2PC_F32 && XD == B2PC_F32) { using S = float; using X = float; CALL; }                 \
+  else if (SD == B2PC_F32 && XD == B2PC_BF16) { using S = float; using X = __nv_bfloat16; CALL; }   \
+  else if (SD == B2PC_F32 && XD == B2PC_F16) { using S = float; using X = __half; CALL; }           \
+  else if (SD == B2PC_BF16 && XD == B2PC_BF16) { using S = __nv_bfloat16; using X = __nv_bfloat16; CALL; } \
+  else if (SD == B2PC_F16 && XD == B2PC_F16) { using S = __half; using X = __half; CALL; }          \
+  else { set_error("rowscale: unsupported dtype pair (%d, %d)", SD, XD); return B2PC_ERR_UNSUPPORTED; }
+
+inline int launch_rowscale_add(const void* shortcut, int sd, const void* x, int xd, const float* rowscale, int64_t n, int c, void* out,
+                               cudaStream_t stream) {
+  B2PC_CHECK_ARG(c % 4 == 0 && c > 0, "rowscale_add: channels %d not a multiple of 4", c);
+  if (n == 0) return B2PC_OK;
+  int64_t b = ceil_div(n * c / 4, 256);
+  if (b > kNumSMs * 16) b = kNumSMs * 16;
+  B2PC_RS_DISPATCH(sd, xd, (rowscale_add_kernel<S, X><<<(int)b, 256, 0, stream>>>((const S*)shortcut, (const X*)x, rowscale, n, c, (S*)out)));
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("rowscale_add");
+  return B2PC_OK;
+}
+// dy in the shortcut/out dtype (sd), dx in x's dtype (xd)
+inline int launch_rowscale(const void* dy, int sd, const float* rowscale, int64_t n, int c, void* dx, int xd, cudaStream_t stream) {
+  B2PC_CHECK_ARG(c % 4 == 0 && c > 0, "rowscale: channels %d not a multiple of 4", c);
+  if (n == 0) return B2PC_OK;
+  int64_t b = ceil_div(n * c / 4, 256);
+  if (b > kNumSMs * 16) b = kNumSMs * 16;
+  B2PC_RS_DISPATCH(sd, xd, (rowscale_kernel<S, X><<<(int)b, 256, 0, stream>>>((const S*)dy, rowscale, n, c, (X*)dx)));
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("rowscale");
+  return B2PC_OK;
+}
+}  // namespace b2pc

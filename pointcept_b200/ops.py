@@ -56,6 +56,22 @@ class _timed:
             _prof.setdefault(self.name, []).append((self.e0, self.e1, self.meta))
 
 
+def binding():
+    """compiled autograd binding (pointcept_b200/csrc/torch_binding.cpp) or None; never used while the per-op profiler runs"""
+    if _prof is not None or _force_ctypes:
+        return None
+    return _lib.torch_binding()
+
+
+_force_ctypes = False
+
+
+def set_binding(name):
+    """"ctypes" forces the Python/ctypes binding (the reference binding), anything else lets the compiled one be used if built."""
+    global _force_ctypes
+    _force_ctypes = name == "ctypes"
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -183,6 +199,9 @@ class PatchAttentionFn(torch.autograd.Function):
 def patch_attention(qkv, cu_seqlens, max_seqlen, scale=None, return_lse=False):
     if scale is None:
         scale = qkv.shape[-1] ** -0.5
+    B = binding()
+    if B is not None and not return_lse:
+        return B.patch_attention(qkv, cu_seqlens, int(max_seqlen), float(scale), _impl)
     out, lse = PatchAttentionFn.apply(qkv, cu_seqlens, max_seqlen, scale)
     return (out, lse) if return_lse else out
 
@@ -305,6 +324,9 @@ class SparseConvFn(torch.autograd.Function):
 
 
 def sparse_conv(feat, weight, bias, table_fwd, table_bwd, flip_bwd):
+    B = binding()
+    if B is not None and feat.dtype in _DTYPES:
+        return B.sparse_conv(feat, weight, bias, table_fwd, table_bwd, bool(flip_bwd), _impl)
     return SparseConvFn.apply(feat, weight, bias, table_fwd, table_bwd, flip_bwd)
 
 
@@ -362,6 +384,9 @@ def layer_norm(x, weight, bias, eps=1e-5, emit_autocast_dtype=False):
         out_dtype = torch.get_autocast_dtype("cuda") if emit_autocast_dtype else torch.float32
     else:
         out_dtype = x.dtype
+    B = binding()
+    if B is not None:
+        return B.layer_norm(x, weight, bias, float(eps), _DTYPES[out_dtype])
     return LayerNormFn.apply(x, weight, bias, eps, out_dtype)
 
 
@@ -399,6 +424,9 @@ class SegmentMaxFn(torch.autograd.Function):
 
 
 def segment_max(x, order, seg_start, seg_len):
+    B = binding()
+    if B is not None:
+        return B.segment_max(x, order, seg_start, seg_len)
     return SegmentMaxFn.apply(x, order, seg_start, seg_len)
 
 
@@ -420,6 +448,9 @@ class UnpoolAddFn(torch.autograd.Function):
 
 
 def unpool_add(parent, child, cluster, order, seg_len):
+    B = binding()
+    if B is not None:
+        return B.unpool_add(parent, child, cluster, order, seg_len)
     return UnpoolAddFn.apply(parent, child, cluster, order, seg_len)
 
 
@@ -480,5 +511,24 @@ def linear(x, weight, bias):
     """F.linear for 2-D CUDA inputs with the fused bias gradient; falls back to F.linear otherwise."""
     if x.is_cuda and x.dim() == 2 and weight.shape[0] % 4 == 0 and x.dtype in _DTYPES:
         cdtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        B = binding()
+        if B is not None:
+            return B.linear(x, weight, bias, _DTYPES[cdtype])
         return LinearFn.apply(x, weight, bias, cdtype)
     return torch.nn.functional.linear(x, weight, bias)
+
+
+def drop_path_add(shortcut, x, drop_prob, training):
+    """shortcut + DropPath(x) (per-row stochastic depth, timm semantics with scale_by_keep) as one kernel when the compiled
+    binding is present; plain torch ops otherwise."""
+    if drop_prob == 0.0 or not training:
+        return shortcut + x
+    keep = 1.0 - drop_prob
+    B = binding()
+    if (B is not None and x.is_cuda and x.dim() == 2 and x.shape[1] % 4 == 0 and shortcut.shape == x.shape
+            and x.dtype in _DTYPES and (shortcut.dtype == torch.float32 or shortcut.dtype == x.dtype)):
+        return B.drop_path_add(shortcut, x, keep)
+    mask = x.new_empty((x.shape[0], 1)).bernoulli_(keep)
+    if keep > 0.0:
+        mask.div_(keep)
+    return shortcut + x * mask

@@ -50,13 +50,16 @@ class FusedLayerNorm(nn.LayerNorm):
 class FusedLinear(nn.Linear):
     """nn.Linear (same parameters).  With ``FusedLinear.use_fused_bias_grad = True`` it routes through ops.linear (identical
     math, fp32 column-sum kernel for the bias gradient: 4.3 -> 1.8 ms of GPU time per PT-v3-base step).  Off by default:
-    at 2 scenes per GPU the step is host-bound and a Python autograd.Function per Linear costs more host time than the
-    kernel saves (measured 48.7 -> 56.5 ms per step); it pays off once the step is GPU-bound (larger per-GPU batches)."""
+    at 2 scenes per GPU the step is host-bound and a *Python* autograd.Function per Linear costs more host time than the
+    kernel saves (measured 48.7 -> 56.5 ms per step), so by default it is used only through the compiled binding."""
 
-    use_fused_bias_grad = False
+    use_fused_bias_grad = None   # None: on exactly when the compiled binding is present (its C++ node is cheaper than autograd's)
 
     def forward(self, x):
-        if FusedLinear.use_fused_bias_grad:
+        on = FusedLinear.use_fused_bias_grad
+        if on is None:
+            on = ops.binding() is not None
+        if on:
             return ops.linear(x, self.weight, self.bias)
         return nn.functional.linear(x, self.weight, self.bias)
 
@@ -147,10 +150,17 @@ class SerializedAttention(PointModule):
         H, K, C = self.num_heads, self.patch_size, self.channels
         _, _, cu_seqlens = self.get_padding_and_inverse(point)
         order_pad, primary_pos, dup_slots, dup_points = self._gather_indices(point)
-        qkv = _SerializedGather.apply(self.qkv(point.feat), order_pad, primary_pos, dup_slots, dup_points)
+        B = ops.binding()
+        if B is not None:
+            qkv = B.serialized_gather(self.qkv(point.feat), order_pad, primary_pos, dup_slots, dup_points)
+        else:
+            qkv = _SerializedGather.apply(self.qkv(point.feat), order_pad, primary_pos, dup_slots, dup_points)
         feat = flash_attn_varlen_qkvpacked_func(qkv.to(torch.bfloat16).reshape(-1, 3, H, C // H), cu_seqlens, max_seqlen=K,
                                                 softmax_scale=self.scale).reshape(-1, C)
-        feat = _SerializedScatterBack.apply(feat.to(qkv.dtype), primary_pos)
+        if B is not None:
+            feat = B.serialized_scatter_back(feat.to(qkv.dtype), primary_pos)
+        else:
+            feat = _SerializedScatterBack.apply(feat.to(qkv.dtype), primary_pos)
         point.feat = self.proj_drop(self.proj(feat))
         return point
 
@@ -201,17 +211,19 @@ class Block(PointModule):
         point = self.cpe(point)
         point.feat = shortcut + point.feat
         shortcut = point.feat
+        dp = self.drop_path[0]
+        dp_prob = dp.drop_prob if isinstance(dp, DropPath) else 0.0
         if self.pre_norm:
             point = self.norm1(point)
-        point = self.drop_path(self.attn(point))
-        point.feat = shortcut + point.feat
+        point = self.attn(point)
+        point.feat = ops.drop_path_add(shortcut, point.feat, dp_prob, self.training)      # shortcut + drop_path(attn)
         if not self.pre_norm:
             point = self.norm1(point)
         shortcut = point.feat
         if self.pre_norm:
             point = self.norm2(point)
-        point = self.drop_path(self.mlp(point))
-        point.feat = shortcut + point.feat
+        point = self.mlp(point)
+        point.feat = ops.drop_path_add(shortcut, point.feat, dp_prob, self.training)      # shortcut + drop_path(mlp)
         if not self.pre_norm:
             point = self.norm2(point)
         point.sparse_conv_feat = point.sparse_conv_feat.replace_feature(point.feat)

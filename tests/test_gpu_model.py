@@ -212,3 +212,47 @@ def test_ptv3_nuscenes_scale_forward_backward_properties():
     assert bool((sorted_codes[:, 1:] > sorted_codes[:, :-1]).all())          # strictly sorted: voxels are unique
     n = sorted_codes.shape[1]
     assert torch.equal(torch.gather(p.serialized_inverse, 1, p.serialized_order), torch.arange(n, device=DEV).expand(4, n))
+
+
+def test_compiled_binding_matches_ctypes_binding(golden_dir):
+    """The pybind/C++ autograd binding and the ctypes/Python binding call the same C ABI: identical results on the tiny model."""
+    from pointcept_b200 import _lib
+    if _lib.torch_binding() is None:
+        pytest.skip("compiled binding not built")
+    g = np.load(os.path.join(golden_dir, "ptv3_tiny.npz"))
+    sd = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}
+    data = dict(coord=torch.from_numpy(g["coord"]).to(DEV), grid_coord=torch.from_numpy(g["grid_coord"]).to(DEV),
+                feat=torch.from_numpy(g["feat"]).to(DEV), offset=torch.from_numpy(g["offset"]).to(DEV))
+    res = {}
+    for name in ("ctypes", "compiled"):
+        ops.set_binding(name)
+        try:
+            model = _tiny_model(sd)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = model(dict(data)).feat
+            out.float().square().mean().backward()
+            res[name] = (out.detach().float(), {k: p.grad.clone() for k, p in model.named_parameters()})
+        finally:
+            ops.set_binding("auto")
+    assert rel_l2(res["compiled"][0], res["ctypes"][0]) < 1e-3
+    for k, gr in res["ctypes"][1].items():
+        # bias gradients go through the fp32 column-sum kernel in the compiled binding (bf16 torch reduction otherwise)
+        tol = 3e-2 if k.endswith("bias") else 5e-3
+        assert rel_l2(res["compiled"][1][k], gr) < tol, k
+
+
+def test_drop_path_add_semantics():
+    torch.manual_seed(0)
+    n, c, p = 20000, 64, 0.3
+    s = torch.randn(n, c, device=DEV)
+    x = torch.randn(n, c, device=DEV).bfloat16().requires_grad_(True)
+    out = ops.drop_path_add(s, x, p, True)
+    delta = out - s
+    dropped = (delta.abs().sum(1) == 0)
+    kept = ~dropped
+    assert abs(float(dropped.float().mean()) - p) < 0.02
+    assert rel_l2(delta[kept], x.detach().float()[kept] / (1 - p)) < 1e-6
+    out.sum().backward()
+    assert torch.equal(x.grad[dropped].float(), torch.zeros_like(x.grad[dropped].float()))
+    assert rel_l2(x.grad[kept].float(), torch.full_like(x.grad[kept].float(), 1 / (1 - p))) < 5e-3
+    assert torch.equal(ops.drop_path_add(s, x.detach(), p, False), s + x.detach())

@@ -13,7 +13,7 @@ def flash_attn_varlen_qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p=0.0,
                                   "(every PT-v3 config sets attn_drop=0.0)")
     if causal or tuple(window_size) != (-1, -1) or softcap != 0.0 or alibi_slopes is not None:
         raise NotImplementedError("pointcept_b200 patch attention: causal/window/softcap/alibi are not supported")
-    out, lse = ops.patch_attention(qkv, cu_seqlens, max_seqlen, softmax_scale, return_lse=True)
     if return_attn_probs:
+        out, lse = ops.patch_attention(qkv, cu_seqlens, max_seqlen, softmax_scale, return_lse=True)
         return out, lse, None
-    return out
+    return ops.patch_attention(qkv, cu_seqlens, max_seqlen, softmax_scale)

@@ -173,7 +173,7 @@ layer_norm_param_reduce_kernel(const float* __restrict__ part_g, const float* __
 
 inline int ln_blocks(int64_t n) {
   int64_t b = ceil_div(n, kLnThreads / 32 * 4);
-  if (b > kNumSMs * 4) b = kNumSMs * 4;
+  if (b > kNumSMs * 2) b = kNumSMs * 2;
   return (int)(b < 1 ? 1 : b);
 }
 inline size_t layer_norm_bwd_workspace_bytes(int64_t n, int c) { return (size_t)ln_blocks(n) * c * 2 * sizeof(float) + 256; }
@@ -264,18 +264,28 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t n, int c, int64_t rows_pe
   }
 }
 
+// one block per 32 channels: 8 warps stride over the chunk partials, fixed-order shared-memory sum at the end
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int chunks, int c, float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  float s = 0.f;
-  for (int b = 0; b < chunks; ++b) s += partial[(int64_t)b * c + ch];
-  out[ch] = s;
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
+  float a = 0.f;
+  if (ch < c)
+    for (int b = grp; b < chunks; b += 8) a += partial[(int64_t)b * c + ch];
+  sm[grp][lane] = a;
+  __syncthreads();
+  if (grp == 0 && ch < c) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    out[ch] = t;
+  }
 }
 
 inline int colsum_chunks(int64_t n, int c) {
   const int slabs = (c + 255) / 256;
-  int64_t chunks = (2 * kNumSMs + slabs - 1) / slabs;
+  int64_t chunks = (kNumSMs + slabs - 1) / slabs;
   const int64_t max_chunks = ceil_div(n > 0 ? n : 1, 64);
   if (chunks > max_chunks) chunks = max_chunks;
   return (int)(chunks < 1 ? 1 : chunks);
@@ -295,7 +305,7 @@ inline int launch_colsum(const void* x, int dtype, int64_t n, int c, float* out,
     case B2PC_BF16: colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, n, c, rpb, (float*)ws); break;
     default: set_error("colsum: unknown dtype %d", dtype); return B2PC_ERR_INVALID_ARG;
   }
-  colsum_final_kernel<<<(c + 255) / 256, 256, 0, stream>>>((const float*)ws, chunks, c, out);
+  colsum_final_kernel<<<(c + 31) / 32, 256, 0, stream>>>((const float*)ws, chunks, c, out);
   count_launches(2);
   B2PC_CHECK_LAUNCH("colsum");
   return B2PC_OK;

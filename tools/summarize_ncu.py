@@ -59,7 +59,7 @@ def launches(csv_path, out, header):
 if __name__ == "__main__":
     launches("gpurun_out/r01_launches.csv", "profiles/r01_ncu_launch_summary.txt",
              "# ncu launch list of one PT-v3m1-base training step (2 x 120k-voxel scenes): bench.py --steps 2 --warmup 3 under\n"
-             "# ncu --metrics gpu__time_duration.sum --clock-control none -s 8600 -c 2900 (cold-cache, serialised: compare SHARES)")
+             "# ncu --metrics gpu__time_duration.sum --clock-control none -s 8000 -c 2700 (cold-cache, serialised: compare SHARES)")
     full("gpurun_out/r01_ncu_attn.ncu-rep", "profiles/r01_ncu_attention_full_metrics.txt",
          "# ncu --set full --clock-control none, tools/probe_attn.py time (H=2, T=241664, K=1024, bf16): attn_fwd_umma_kernel (TMA path)")
     full("gpurun_out/r01_ncu_conv.ncu-rep", "profiles/r01_ncu_conv_full_metrics.txt",

@@ -9,7 +9,6 @@
 namespace b2pc {
 
 constexpr int kLnThreads = 256;
-constexpr int kLnMaxPerLane = 16;   // C <= 512
 
 // ---- vector access: 4 consecutive channels per lane -----------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float4 ld4(const T* p);

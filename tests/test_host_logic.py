@@ -60,6 +60,16 @@ def test_unmodified_reference_models_build_on_the_dropins_with_identical_state_d
     a = {k: tuple(v.shape) for k, v in SpUNetBase(6, 20).state_dict().items()}
     b = {k: tuple(v.shape) for k, v in ref.spunet.SpUNetBase(6, 20).state_dict().items()}
     assert a == b and len(a) > 300
+    # the reference's own Point.sparsify() (structure.py:112-148) builds OUR SparseConvTensor, and its PointSequential
+    # (modules.py:84) recognises our conv modules through spconv.modules.is_spconv_module
+    import spconv.pytorch as spconv
+    pt = ref.structure.Point(grid_coord=torch.randint(0, 50, (100, 3)), feat=torch.randn(100, 6), offset=torch.tensor([60, 100]))
+    pt.sparsify()
+    x = pt.sparse_conv_feat
+    assert isinstance(x, spconv.SparseConvTensor) and x.indices.dtype == torch.int32 and x.batch_size == 2
+    assert x.spatial_shape == [int(v) + 96 for v in pt.grid_coord.max(0).values]
+    seq = ref.modules.PointSequential(spconv.SubMConv3d(6, 8, 3, indice_key="k"))
+    assert spconv.modules.is_spconv_module(seq[0])
     for k in [k for k in sys.modules if k.split(".")[0] in ("spconv", "flash_attn", "pointcept", "addict", "timm", "torch_scatter", "torch_geometric")]:
         del sys.modules[k]
 
@@ -129,6 +139,13 @@ def test_two_rank_gloo_sharding_and_reductions(tmp_path):
     assert r["points"] == 2 * 1500 + 2 * 1600       # different scenes per rank, whole scenes only
     assert r["ms"] == 15.0                           # max over ranks
     assert abs(r["grad"] - 3 * (1 + 2) / 2) < 1e-6   # DDP averages gradients
+
+
+def test_bench_reference_arm_is_silent_on_other_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
 
 
 def test_bench_reference_arm_prints_one_json_line():

@@ -100,6 +100,37 @@ class _SerializedScatterBack(torch.autograd.Function):
         return dx, None
 
 
+def borrowed_slots(offset_host, K, device):
+    """Padded slots that hold a BORROWED token (the last K - n%K slots of a padded scene repeat the K - n%K tokens in front of
+    the scene's last patch, ptv3m1:144-154); host arithmetic on the scene sizes, no sync."""
+    slots, op = [], 0
+    for a, b in zip([0] + list(offset_host[:-1]), offset_host):
+        n = b - a
+        npad = ((n + K - 1) // K * K) if n > K else n
+        if npad != n:
+            slots.append(torch.arange(op + npad - (K - n % K), op + npad, device=device))
+        op += npad
+    return torch.cat(slots) if slots else torch.zeros(0, dtype=torch.long, device=device)
+
+
+def serialized_gather(x, order_pad, primary_pos, offset_host, K, dup=None):
+    """x[order_pad] with the structured (sort-free) backward; compiled node when the binding is built."""
+    if dup is None:
+        ds = borrowed_slots(offset_host, K, x.device)
+        dup = (ds, order_pad[ds])
+    B = ops.binding()
+    if B is not None:
+        return B.serialized_gather(x, order_pad, primary_pos, dup[0], dup[1])
+    return _SerializedGather.apply(x, order_pad, primary_pos, dup[0], dup[1])
+
+
+def serialized_scatter_back(x_pad, primary_pos):
+    B = ops.binding()
+    if B is not None:
+        return B.serialized_scatter_back(x_pad, primary_pos)
+    return _SerializedScatterBack.apply(x_pad, primary_pos)
+
+
 class SerializedAttention(PointModule):
     """ptv3m1:51-222 (flash branch only: RPE / upcast options belong to the non-flash fallback)."""
 
@@ -133,16 +164,7 @@ class SerializedAttention(PointModule):
             pad, unpad, _ = self.get_padding_and_inverse(point)
             order_pad = point.serialized_order[self.order_index][pad]
             primary_pos = unpad[point.serialized_inverse[self.order_index]]
-            # borrowed filler slots of each padded scene: the last K - n%K slots of its padded range (host arithmetic, no sync)
-            K, oh = self.patch_size, point.host_offset()
-            slots, op = [], 0
-            for a, b in zip([0] + list(oh[:-1]), oh):
-                n = b - a
-                npad = ((n + K - 1) // K * K) if n > K else n
-                if npad != n:
-                    slots.append(torch.arange(op + npad - (K - n % K), op + npad, device=pad.device))
-                op += npad
-            dup_slots = torch.cat(slots) if slots else pad.new_zeros(0)
+            dup_slots = borrowed_slots(point.host_offset(), self.patch_size, pad.device)
             point[key] = (order_pad, primary_pos, dup_slots, order_pad[dup_slots])
         return point[key]
 
@@ -150,17 +172,11 @@ class SerializedAttention(PointModule):
         H, K, C = self.num_heads, self.patch_size, self.channels
         _, _, cu_seqlens = self.get_padding_and_inverse(point)
         order_pad, primary_pos, dup_slots, dup_points = self._gather_indices(point)
-        B = ops.binding()
-        if B is not None:
-            qkv = B.serialized_gather(self.qkv(point.feat), order_pad, primary_pos, dup_slots, dup_points)
-        else:
-            qkv = _SerializedGather.apply(self.qkv(point.feat), order_pad, primary_pos, dup_slots, dup_points)
+        qkv = serialized_gather(self.qkv(point.feat), order_pad, primary_pos, None, K, dup=(dup_slots, dup_points))
+        # bf16 at the operator boundary whatever the autocast dtype, exactly as the reference (ptv3m1:209)
         feat = flash_attn_varlen_qkvpacked_func(qkv.to(torch.bfloat16).reshape(-1, 3, H, C // H), cu_seqlens, max_seqlen=K,
                                                 softmax_scale=self.scale).reshape(-1, C)
-        if B is not None:
-            feat = B.serialized_scatter_back(feat.to(qkv.dtype), primary_pos)
-        else:
-            feat = _SerializedScatterBack.apply(feat.to(qkv.dtype), primary_pos)
+        feat = serialized_scatter_back(feat.to(qkv.dtype), primary_pos)
         point.feat = self.proj_drop(self.proj(feat))
         return point
 

@@ -12,6 +12,7 @@
 #ifndef B2PC_NO_UMMA
 #include "attn_umma.cuh"
 #include "spconv_umma.cuh"
+#include "spconv_ws.cuh"
 #endif
 
 #include <atomic>
@@ -29,6 +30,12 @@ void set_error(const char* fmt, ...) {
 }  // namespace b2pc
 
 using namespace b2pc;
+
+// B2PC_CONV_V1=1 selects the first-generation (round 1) tcgen05 sparse-conv kernels for A/B runs
+static bool conv_v1() {
+  static const bool v = [] { const char* e = getenv("B2PC_CONV_V1"); return e && atoi(e) != 0; }();
+  return v;
+}
 
 extern "C" {
 
@@ -130,6 +137,7 @@ int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* s
 // ---- sparse convolution arithmetic ---------------------------------------------------------------------
 size_t b2pc_spconv_gather_gemm_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
 #ifndef B2PC_NO_UMMA
+  if (!conv_v1()) return 0;
   return conv_umma_workspace_bytes(n_out, c_in, c_out, kv);
 #else
   return 0;
@@ -144,6 +152,8 @@ int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bi
   cudaStream_t s = (cudaStream_t)stream;
 #ifndef B2PC_NO_UMMA
   if (impl != 1) {
+    if (!conv_v1() && conv_ws_supported(dtype, c_in, c_out, kv))
+      return launch_conv_ws(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, dtype, out, s);
     if (spconv_umma_supported(dtype, c_in, c_out)) {
       const size_t need = conv_umma_workspace_bytes(n_out, c_in, c_out, kv);
       if (need > 0 && (!workspace || workspace_bytes < need)) { set_error("spconv_gather_gemm: workspace too small"); return B2PC_ERR_WORKSPACE; }
@@ -166,7 +176,9 @@ int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bi
 size_t b2pc_spconv_bwd_weight_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
   size_t b = bwd_weight_workspace_bytes(n_out, c_in, c_out, kv);
 #ifndef B2PC_NO_UMMA
-  const size_t u = wgrad_umma_workspace_bytes(n_out, c_in, c_out, kv);
+  size_t u = wgrad_umma_workspace_bytes(n_out, c_in, c_out, kv);
+  if (u > b) b = u;
+  u = wgrad_ws_workspace_bytes(n_out, c_in, c_out, kv);
   if (u > b) b = u;
 #endif
   return b;
@@ -181,6 +193,8 @@ int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t*
   if (workspace_bytes < b2pc_spconv_bwd_weight_workspace_bytes(n_out, c_in, c_out, kv)) { set_error("spconv_bwd_weight: workspace too small"); return B2PC_ERR_WORKSPACE; }
 #ifndef B2PC_NO_UMMA
   if (impl != 1 && n_out > 0) {
+    if (!conv_v1() && wgrad_ws_supported(dtype, c_in, c_out, kv))
+      return launch_wgrad_ws(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dtype, dweight, workspace, s);
     if (wgrad_umma_supported(dtype, c_in, c_out)) return launch_bwd_weight_umma(feat_in, dout, pair, pair_stride, n_out, c_in, c_out, kv, dtype, dweight, workspace, s);
     if (impl == 2) { set_error("spconv_bwd_weight: tcgen05 kernel does not support dtype %d c_in %d c_out %d", dtype, c_in, c_out); return B2PC_ERR_UNSUPPORTED; }
   }

@@ -184,6 +184,36 @@ size_t b2pc_colsum_workspace_bytes(int64_t n, int c);
 int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* workspace, size_t workspace_bytes,
                 b2pc_stream_t stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused residual glue of one PT-v3 block (point_transformer_v3m1_base.py:318-338):
+ *     t = x;  t = LayerNorm_a(t) [gamma_a != NULL];  t *= (u[row] < keep ? 1/keep : 0) [u != NULL, DropPath :313-315]
+ *     r = shortcut + t (fp32, written);  r16 = (dtype) r [r16 != NULL];  y = LayerNorm_b(r) in dtype [gamma_b != NULL]
+ * x / r16 / y are `dtype` (fp32, fp16 or bf16), shortcut / r / statistics / affine parameters fp32.
+ * stat_a / stat_b: [2, n] (mean, rstd) saved for the backward.  C in {32, 64, 128, 256, 512}.
+ * Backward: exact adjoint.  dr_out / dr16 / dy are the gradients of the three outputs (any may be NULL);
+ * d_shortcut [n,c] fp32 and dx [n,c] dtype are written; the LayerNorm parameter gradients are reduced deterministically.
+ * ------------------------------------------------------------------------------------------- */
+int b2pc_fused_residual_fwd(const float* shortcut, const void* x, int dtype, const float* u, float keep,
+                            const float* gamma_a, const float* beta_a, float eps_a, const float* gamma_b,
+                            const float* beta_b, float eps_b, int64_t n, int c, float* r, void* r16, void* y,
+                            float* stat_a, float* stat_b, b2pc_stream_t stream);
+size_t b2pc_fused_residual_bwd_workspace_bytes(int64_t n, int c);
+int b2pc_fused_residual_bwd(const float* dr_out, const void* dr16, const void* dy, int dtype, const float* r,
+                            const void* x, const float* u, float keep, const float* gamma_a, const float* gamma_b,
+                            const float* stat_a, const float* stat_b, int64_t n, int c, float* d_shortcut, void* dx,
+                            float* dgamma_a, float* dbeta_a, float* dgamma_b, float* dbeta_b, void* workspace,
+                            size_t workspace_bytes, b2pc_stream_t stream);
+
+/* One launch refreshes the half-precision shadows of a list of fp32 parameter tensors (what autocast does with one cast
+ * kernel per weight per step, torch/amp).  plan: DEVICE array of n_items records {const float* src; void* dst;
+ * long long count; long long first_block} with first_block the running sum of ceil(count / 2048); total_blocks its end. */
+int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks, int dst_dtype, b2pc_stream_t stream);
+
+/* Exact (erf) GELU over n_elems values (n_elems % 4 == 0), forward and backward (nn.GELU, point_transformer_v3m1_base.py:233). */
+int b2pc_gelu_fwd(const void* x, int dtype, int64_t n_elems, void* y, b2pc_stream_t stream);
+int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, void* dx, b2pc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 #include "spconv_simt.cuh"
 #include "attn_simt.cuh"
 #include "layernorm.cuh"
+#include "fused.cuh"
 #include "pool.cuh"
 #ifndef B2PC_NO_UMMA
 #include "attn_umma.cuh"
@@ -257,6 +258,65 @@ size_t b2pc_colsum_workspace_bytes(int64_t n, int c) { return colsum_workspace_b
 int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
   B2PC_CHECK_ARG(x && out && workspace, "colsum: null pointer");
   return launch_colsum(x, dtype, n, c, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- fused residual glue ------------------------------------------------------------------------------------------------
+int b2pc_fused_residual_fwd(const float* shortcut, const void* x, int dtype, const float* u, float keep, const float* gamma_a,
+                            const float* beta_a, float eps_a, const float* gamma_b, const float* beta_b, float eps_b, int64_t n, int c,
+                            float* r, void* r16, void* y, float* stat_a, float* stat_b, b2pc_stream_t stream) {
+  FusedResArgs a{shortcut, x, u, keep, gamma_a, beta_a, gamma_b, beta_b, eps_a, eps_b, n, c, r, r16, y, stat_a, stat_b};
+  return launch_fused_residual_fwd(a, dtype, (cudaStream_t)stream);
+}
+
+size_t b2pc_fused_residual_bwd_workspace_bytes(int64_t n, int c) { return fused_residual_bwd_workspace_bytes(n, c); }
+
+int b2pc_fused_residual_bwd(const float* dr_out, const void* dr16, const void* dy, int dtype, const float* r, const void* x,
+                            const float* u, float keep, const float* gamma_a, const float* gamma_b, const float* stat_a,
+                            const float* stat_b, int64_t n, int c, float* d_shortcut, void* dx, float* dgamma_a, float* dbeta_a,
+                            float* dgamma_b, float* dbeta_b, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  FusedResBwdArgs a{dr_out, dr16, dy, r, x, u, keep, gamma_a, gamma_b, stat_a, stat_b, n, c, d_shortcut, dx, nullptr};
+  return launch_fused_residual_bwd(a, dtype, dgamma_a, dbeta_a, dgamma_b, dbeta_b, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks, int dst_dtype, b2pc_stream_t stream) {
+  return launch_multi_cast(plan_device, n_items, total_blocks, dst_dtype, (cudaStream_t)stream);
+}
+
+static int gelu_grid(int64_t total4) {
+  int64_t b = ceil_div(total4 > 0 ? total4 : 1, 256);
+  return (int)(b > kNumSMs * 16 ? kNumSMs * 16 : b);
+}
+
+int b2pc_gelu_fwd(const void* x, int dtype, int64_t n_elems, void* y, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(x && y && n_elems >= 0 && n_elems % 4 == 0, "gelu_fwd: bad arguments");
+  if (n_elems == 0) return B2PC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t t4 = n_elems / 4;
+  switch (dtype) {
+    case B2PC_F32: gelu_fwd_kernel<float><<<gelu_grid(t4), 256, 0, s>>>((const float*)x, t4, (float*)y); break;
+    case B2PC_F16: gelu_fwd_kernel<__half><<<gelu_grid(t4), 256, 0, s>>>((const __half*)x, t4, (__half*)y); break;
+    case B2PC_BF16: gelu_fwd_kernel<__nv_bfloat16><<<gelu_grid(t4), 256, 0, s>>>((const __nv_bfloat16*)x, t4, (__nv_bfloat16*)y); break;
+    default: set_error("gelu_fwd: unknown dtype %d", dtype); return B2PC_ERR_INVALID_ARG;
+  }
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("gelu_fwd");
+  return B2PC_OK;
+}
+
+int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, void* dx, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(dy && x && dx && n_elems >= 0 && n_elems % 4 == 0, "gelu_bwd: bad arguments");
+  if (n_elems == 0) return B2PC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t t4 = n_elems / 4;
+  switch (dtype) {
+    case B2PC_F32: gelu_bwd_kernel<float><<<gelu_grid(t4), 256, 0, s>>>((const float*)dy, (const float*)x, t4, (float*)dx); break;
+    case B2PC_F16: gelu_bwd_kernel<__half><<<gelu_grid(t4), 256, 0, s>>>((const __half*)dy, (const __half*)x, t4, (__half*)dx); break;
+    case B2PC_BF16: gelu_bwd_kernel<__nv_bfloat16><<<gelu_grid(t4), 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, t4, (__nv_bfloat16*)dx); break;
+    default: set_error("gelu_bwd: unknown dtype %d", dtype); return B2PC_ERR_INVALID_ARG;
+  }
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("gelu_bwd");
+  return B2PC_OK;
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 // Why it exists: the PT-v3 step at 2 scenes per GPU is host-bound; a Python autograd.Function costs ~25 us per direction,
 // the same node in C++ a few.
 #include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
 #include "../../include/b2pc.h"
@@ -33,11 +34,21 @@ inline Tensor workspace(size_t bytes, const Tensor& like) {
   return at::empty({(int64_t)(bytes > 0 ? bytes : 1)}, like.options().dtype(at::kByte));
 }
 inline void need_cuda(const Tensor& t) { TORCH_CHECK(t.is_cuda(), "pointcept_b200 operators run on CUDA tensors only; there is no CPU fallback"); }
+// every entry point pins the device of its tensors: the launch goes to the GPU that owns the data and to that GPU's current stream
+#define B2PC_GUARD(t) need_cuda(t); const c10::cuda::CUDAGuard device_guard__((t).device())
+inline const void* optr(const Tensor& t) { return t.defined() ? t.data_ptr() : nullptr; }
+inline const float* fptr(const Tensor& t) { return t.defined() ? t.data_ptr<float>() : nullptr; }
+inline Tensor f32c(const c10::optional<Tensor>& t) {
+  if (!t.has_value() || !t->defined()) return Tensor();
+  Tensor v = t->detach();
+  if (v.scalar_type() != at::kFloat || !v.is_contiguous()) v = v.to(at::kFloat).contiguous();
+  return v;
+}
 
 // ---- LayerNorm ----------------------------------------------------------------------------------------------------------
 struct LayerNormFn : public torch::autograd::Function<LayerNormFn> {
   static Tensor forward(AutogradContext* ctx, Tensor x, Tensor weight, c10::optional<Tensor> bias, double eps, int64_t out_code) {
-    need_cuda(x);
+    B2PC_GUARD(x);
     x = x.contiguous();
     const int64_t n = x.size(0), c = x.size(1);
     Tensor w = weight.detach();
@@ -60,6 +71,7 @@ struct LayerNormFn : public torch::autograd::Function<LayerNormFn> {
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     auto saved = ctx->get_saved_variables();
     Tensor x = saved[0], w = saved[1], mean = saved[2], rstd = saved[3];
+    B2PC_GUARD(x);
     Tensor dy = grads[0].contiguous();
     const int64_t n = x.size(0), c = x.size(1);
     const bool has_bias = ctx->saved_data["has_bias"].toBool();
@@ -111,7 +123,7 @@ struct SerializedScatterBackFn : public torch::autograd::Function<SerializedScat
 // ---- patch attention ----------------------------------------------------------------------------------------------------------
 struct PatchAttentionFn : public torch::autograd::Function<PatchAttentionFn> {
   static Tensor forward(AutogradContext* ctx, Tensor qkv, Tensor cu, int64_t max_seqlen, double scale, int64_t impl) {
-    need_cuda(qkv);
+    B2PC_GUARD(qkv);
     TORCH_CHECK(qkv.scalar_type() == at::kHalf || qkv.scalar_type() == at::kBFloat16, "patch attention takes fp16 or bf16 qkv");
     qkv = qkv.contiguous();
     if (cu.scalar_type() != at::kInt) cu = cu.to(at::kInt);
@@ -131,6 +143,7 @@ struct PatchAttentionFn : public torch::autograd::Function<PatchAttentionFn> {
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     auto s = ctx->get_saved_variables();
     Tensor qkv = s[0], out = s[1], lse = s[2], cu = s[3];
+    B2PC_GUARD(qkv);
     Tensor dout = grads[0].contiguous();
     const int64_t T = qkv.size(0), H = qkv.size(2), D = qkv.size(3);
     Tensor dqkv = at::empty_like(qkv);
@@ -158,16 +171,22 @@ Tensor gather_gemm(const Tensor& feat, const Tensor& w, const Tensor& bias, cons
 }
 
 struct SparseConvFn : public torch::autograd::Function<SparseConvFn> {
+  // w16 / b16: optional half-precision shadows of weight / bias kept fresh by the cast plan (no per-call cast kernels)
   static Tensor forward(AutogradContext* ctx, Tensor feat, Tensor weight, c10::optional<Tensor> bias, Tensor table_fwd, Tensor table_bwd,
-                        bool flip_bwd, int64_t impl) {
-    need_cuda(feat);
+                        bool flip_bwd, int64_t impl, c10::optional<Tensor> w16, c10::optional<Tensor> b16) {
+    B2PC_GUARD(feat);
     feat = feat.contiguous();
     const int c_out = (int)weight.size(0), kv = (int)weight.size(1), c_in = (int)weight.size(2);
     TORCH_CHECK(feat.size(1) == c_in, "sparse conv: feature width ", feat.size(1), " != weight input channels ", c_in);
-    Tensor w = weight.detach().to(feat.scalar_type()).contiguous();
+    Tensor w;
+    if (w16.has_value() && w16->defined() && w16->scalar_type() == feat.scalar_type()) w = w16->view({c_out, kv, c_in});
+    else w = weight.detach().to(feat.scalar_type()).contiguous();
     Tensor b;
     const bool has_bias = bias.has_value() && bias->defined();
-    if (has_bias) b = bias->detach().to(feat.scalar_type()).contiguous();
+    if (has_bias) {
+      if (b16.has_value() && b16->defined() && b16->scalar_type() == feat.scalar_type()) b = *b16;
+      else b = bias->detach().to(feat.scalar_type()).contiguous();
+    }
     Tensor out = gather_gemm(feat, w, b, table_fwd, table_fwd.size(1), c_in, c_out, kv, false, false, (int)impl);
     ctx->save_for_backward({feat, w, table_fwd, table_bwd});
     ctx->saved_data["flip_bwd"] = flip_bwd;
@@ -179,6 +198,7 @@ struct SparseConvFn : public torch::autograd::Function<SparseConvFn> {
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     auto s = ctx->get_saved_variables();
     Tensor feat = s[0], w = s[1], table_fwd = s[2], table_bwd = s[3];
+    B2PC_GUARD(feat);
     const int c_out = (int)w.size(0), kv = (int)w.size(1), c_in = (int)w.size(2);
     const int impl = (int)ctx->saved_data["impl"].toInt();
     Tensor dout = grads[0].contiguous();
@@ -197,15 +217,24 @@ struct SparseConvFn : public torch::autograd::Function<SparseConvFn> {
       const auto wd = (at::ScalarType)ctx->saved_data["wdtype"].toInt();
       if (wd != at::kFloat) dweight = dweight.to(wd);
     }
-    if (ctx->saved_data["has_bias"].toBool() && ctx->needs_input_grad(2)) dbias = dout.to(at::kFloat).sum(0);
-    return {dfeat, dweight, dbias, Tensor(), Tensor(), Tensor(), Tensor()};
+    if (ctx->saved_data["has_bias"].toBool() && ctx->needs_input_grad(2)) {
+      if (c_out % 4 == 0 && dout.size(0) > 0) {
+        dbias = at::empty({c_out}, dout.options().dtype(at::kFloat));
+        Tensor ws = workspace(b2pc_colsum_workspace_bytes(dout.size(0), c_out), dout);
+        check(b2pc_colsum(dout.data_ptr(), dt(dout), dout.size(0), c_out, dbias.data_ptr<float>(), ws.data_ptr(), (size_t)ws.numel(), cur_stream()),
+              "colsum");
+      } else {
+        dbias = dout.to(at::kFloat).sum(0);
+      }
+    }
+    return {dfeat, dweight, dbias, Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
   }
 };
 
 // ---- pooling ------------------------------------------------------------------------------------------------------------------------
 struct SegmentMaxFn : public torch::autograd::Function<SegmentMaxFn> {
   static Tensor forward(AutogradContext* ctx, Tensor x, Tensor order, Tensor seg_start, Tensor seg_len) {
-    need_cuda(x);
+    B2PC_GUARD(x);
     x = x.contiguous();
     const int64_t n = x.size(0), c = x.size(1), m = seg_start.size(0);
     Tensor out = at::empty({m, c}, x.options());
@@ -219,6 +248,7 @@ struct SegmentMaxFn : public torch::autograd::Function<SegmentMaxFn> {
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     Tensor arg = ctx->get_saved_variables()[0];
+    B2PC_GUARD(arg);
     Tensor dout = grads[0].contiguous();
     const int64_t n = ctx->saved_data["n"].toInt(), m = arg.size(0), c = arg.size(1);
     Tensor dx = at::empty({n, c}, dout.options());
@@ -246,13 +276,20 @@ struct UnpoolAddFn : public torch::autograd::Function<UnpoolAddFn> {
 
 // ---- Linear with the fused fp32 bias-gradient reduction --------------------------------------------------------------------------------
 struct LinearFn : public torch::autograd::Function<LinearFn> {
-  static Tensor forward(AutogradContext* ctx, Tensor x, Tensor weight, c10::optional<Tensor> bias, int64_t ccode) {
+  static Tensor forward(AutogradContext* ctx, Tensor x, Tensor weight, c10::optional<Tensor> bias, int64_t ccode, c10::optional<Tensor> w16,
+                        c10::optional<Tensor> b16) {
+    B2PC_GUARD(x);
     const auto cd = st((int)ccode);
     Tensor xc = x.scalar_type() == cd ? x : x.to(cd);
-    Tensor wc = weight.scalar_type() == cd ? weight : weight.to(cd);
+    Tensor wc;
+    if (w16.has_value() && w16->defined() && w16->scalar_type() == cd) wc = *w16;
+    else wc = weight.scalar_type() == cd ? weight.detach() : weight.detach().to(cd);
     const bool has_bias = bias.has_value() && bias->defined();
     Tensor bc;
-    if (has_bias) bc = bias->scalar_type() == cd ? *bias : bias->to(cd);
+    if (has_bias) {
+      if (b16.has_value() && b16->defined() && b16->scalar_type() == cd) bc = *b16;
+      else bc = bias->scalar_type() == cd ? bias->detach() : bias->detach().to(cd);
+    }
     Tensor y;
     {
       at::AutoDispatchBelowADInplaceOrView guard;
@@ -267,12 +304,20 @@ struct LinearFn : public torch::autograd::Function<LinearFn> {
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     auto s = ctx->get_saved_variables();
     Tensor xc = s[0], wc = s[1];
+    B2PC_GUARD(xc);
     Tensor dy = grads[0].contiguous();
     Tensor dx, dw, db;
     const auto xd = (at::ScalarType)ctx->saved_data["xd"].toInt(), wd = (at::ScalarType)ctx->saved_data["wd"].toInt();
     const int64_t bd = ctx->saved_data["bd"].toInt();
     if (ctx->needs_input_grad(0)) { dx = at::mm(dy, wc); if (dx.scalar_type() != xd) dx = dx.to(xd); }
-    if (ctx->needs_input_grad(1)) { dw = at::mm(dy.t(), xc); if (dw.scalar_type() != wd) dw = dw.to(wd); }
+    if (ctx->needs_input_grad(1)) {
+      // half-precision operands, fp32 accumulate AND fp32 result straight from the GEMM (no bf16 rounding of dW, no cast kernel)
+      static bool mm_dtype_ok = true;
+      if (wd == at::kFloat && dy.scalar_type() != at::kFloat && mm_dtype_ok) {
+        try { dw = at::mm(dy.t(), xc, at::kFloat); } catch (const c10::Error&) { mm_dtype_ok = false; }
+      }
+      if (!dw.defined()) { dw = at::mm(dy.t(), xc); if (dw.scalar_type() != wd) dw = dw.to(wd); }
+    }
     if (bd >= 0 && ctx->needs_input_grad(2)) {
       const int64_t n = dy.size(0), c = dy.size(1);
       db = at::empty({c}, dy.options().dtype(at::kFloat));
@@ -280,14 +325,121 @@ struct LinearFn : public torch::autograd::Function<LinearFn> {
       check(b2pc_colsum(dy.data_ptr(), dt(dy), n, (int)c, db.data_ptr<float>(), ws.data_ptr(), (size_t)ws.numel(), cur_stream()), "colsum");
       if ((at::ScalarType)bd != at::kFloat) db = db.to((at::ScalarType)bd);
     }
-    return {dx, dw, db, Tensor()};
+    return {dx, dw, db, Tensor(), Tensor(), Tensor()};
   }
 };
+
+// ---- fused residual glue (csrc/fused.cuh): [LayerNorm_a] -> [DropPath scale] -> + shortcut -> [half copy] -> [LayerNorm_b] ---------------
+struct FusedResidualFn : public torch::autograd::Function<FusedResidualFn> {
+  // returns {r} + ({r16} if emit_half) + ({y} if LayerNorm_b); flags are recoverable from the argument list
+  static variable_list forward(AutogradContext* ctx, Tensor shortcut, Tensor x, c10::optional<Tensor> u, double keep,
+                               c10::optional<Tensor> ga, c10::optional<Tensor> ba, double eps_a, c10::optional<Tensor> gb,
+                               c10::optional<Tensor> bb, double eps_b, bool emit_half) {
+    B2PC_GUARD(x);
+    TORCH_CHECK(shortcut.scalar_type() == at::kFloat, "fused_residual: the residual stream is fp32");
+    shortcut = shortcut.contiguous();
+    x = x.contiguous();
+    const int64_t n = x.size(0), c = x.size(1);
+    Tensor gaf = f32c(ga), baf = f32c(ba), gbf = f32c(gb), bbf = f32c(bb);
+    Tensor uf = (u.has_value() && u->defined()) ? u->contiguous() : Tensor();
+    Tensor r = at::empty({n, c}, x.options().dtype(at::kFloat));
+    Tensor r16 = emit_half ? at::empty({n, c}, x.options()) : Tensor();
+    Tensor y = gbf.defined() ? at::empty({n, c}, x.options()) : Tensor();
+    Tensor sa = gaf.defined() ? at::empty({2, n}, x.options().dtype(at::kFloat)) : Tensor();
+    Tensor sb = gbf.defined() ? at::empty({2, n}, x.options().dtype(at::kFloat)) : Tensor();
+    check(b2pc_fused_residual_fwd(shortcut.data_ptr<float>(), x.data_ptr(), dt(x), fptr(uf), (float)keep, fptr(gaf), fptr(baf), (float)eps_a,
+                                  fptr(gbf), fptr(bbf), (float)eps_b, n, (int)c, r.data_ptr<float>(), r16.defined() ? r16.data_ptr() : nullptr,
+                                  y.defined() ? y.data_ptr() : nullptr, sa.defined() ? sa.data_ptr<float>() : nullptr,
+                                  sb.defined() ? sb.data_ptr<float>() : nullptr, cur_stream()),
+          "fused_residual_fwd");
+    ctx->save_for_backward({x, r, uf, gaf, gbf, sa, sb});
+    ctx->saved_data["keep"] = keep;
+    ctx->saved_data["emit_half"] = emit_half;
+    ctx->saved_data["has_ba"] = baf.defined();
+    ctx->saved_data["has_bb"] = bbf.defined();
+    variable_list outs{r};
+    if (emit_half) outs.push_back(r16);
+    if (y.defined()) outs.push_back(y);
+    return outs;
+  }
+  static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    auto s = ctx->get_saved_variables();
+    Tensor x = s[0], r = s[1], uf = s[2], gaf = s[3], gbf = s[4], sa = s[5], sb = s[6];
+    B2PC_GUARD(x);
+    const bool emit_half = ctx->saved_data["emit_half"].toBool();
+    const int64_t n = x.size(0), c = x.size(1);
+    size_t gi = 0;
+    Tensor dr_out = grads[gi++], dr16, dy;
+    if (emit_half) dr16 = grads[gi++];
+    if (gbf.defined()) dy = grads[gi++];
+    if (dr_out.defined()) dr_out = dr_out.to(at::kFloat).contiguous();
+    if (dr16.defined()) dr16 = dr16.to(x.scalar_type()).contiguous();
+    if (dy.defined()) dy = dy.to(x.scalar_type()).contiguous();
+    Tensor d_shortcut = at::empty({n, c}, x.options().dtype(at::kFloat));
+    Tensor dx = at::empty_like(x);
+    Tensor dga, dba, dgb, dbb;
+    if (gaf.defined()) { dga = at::empty({c}, r.options()); dba = at::empty({c}, r.options()); }
+    if (gbf.defined()) { dgb = at::empty({c}, r.options()); dbb = at::empty({c}, r.options()); }
+    Tensor ws = workspace(b2pc_fused_residual_bwd_workspace_bytes(n, (int)c), x);
+    check(b2pc_fused_residual_bwd(fptr(dr_out), optr(dr16), optr(dy), dt(x), r.data_ptr<float>(), x.data_ptr(), fptr(uf),
+                                  (float)ctx->saved_data["keep"].toDouble(), fptr(gaf), fptr(gbf), fptr(sa), fptr(sb), n, (int)c,
+                                  d_shortcut.data_ptr<float>(), dx.data_ptr(), dga.defined() ? dga.data_ptr<float>() : nullptr,
+                                  dba.defined() ? dba.data_ptr<float>() : nullptr, dgb.defined() ? dgb.data_ptr<float>() : nullptr,
+                                  dbb.defined() ? dbb.data_ptr<float>() : nullptr, ws.data_ptr(), (size_t)ws.numel(), cur_stream()),
+          "fused_residual_bwd");
+    if (!ctx->saved_data["has_ba"].toBool()) dba = Tensor();
+    if (!ctx->saved_data["has_bb"].toBool()) dbb = Tensor();
+    return {d_shortcut, dx, Tensor(), Tensor(), dga, dba, Tensor(), dgb, dbb, Tensor(), Tensor()};
+  }
+};
+
+// ---- exact GELU --------------------------------------------------------------------------------------------------------------------------
+struct GeluFn : public torch::autograd::Function<GeluFn> {
+  static Tensor forward(AutogradContext* ctx, Tensor x) {
+    B2PC_GUARD(x);
+    x = x.contiguous();
+    Tensor y = at::empty_like(x);
+    check(b2pc_gelu_fwd(x.data_ptr(), dt(x), x.numel(), y.data_ptr(), cur_stream()), "gelu_fwd");
+    ctx->save_for_backward({x});
+    return y;
+  }
+  static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    Tensor x = ctx->get_saved_variables()[0];
+    B2PC_GUARD(x);
+    Tensor dy = grads[0].contiguous();
+    if (dy.scalar_type() != x.scalar_type()) dy = dy.to(x.scalar_type());
+    Tensor dx = at::empty_like(x);
+    check(b2pc_gelu_bwd(dy.data_ptr(), x.data_ptr(), dt(x), x.numel(), dx.data_ptr(), cur_stream()), "gelu_bwd");
+    return {dx};
+  }
+};
+
+// ---- half-precision parameter shadows: one launch per step instead of one cast kernel per weight ------------------------------------------
+struct CastRecord { const float* src; void* dst; long long count; long long first_block; };
+// -> (plan tensor on the parameters' device, n_items, total_blocks)
+std::tuple<Tensor, int64_t, int64_t> make_cast_plan(std::vector<Tensor> params, std::vector<Tensor> shadows) {
+  TORCH_CHECK(params.size() == shadows.size() && !params.empty(), "cast plan: parameter / shadow lists differ");
+  std::vector<CastRecord> rec(params.size());
+  long long blocks = 0;
+  for (size_t i = 0; i < params.size(); ++i) {
+    TORCH_CHECK(params[i].is_cuda() && params[i].scalar_type() == at::kFloat && params[i].is_contiguous() && shadows[i].is_contiguous() &&
+                    params[i].numel() == shadows[i].numel(), "cast plan: parameters must be contiguous fp32 CUDA tensors with same-size shadows");
+    rec[i] = CastRecord{params[i].data_ptr<float>(), shadows[i].data_ptr(), (long long)params[i].numel(), blocks};
+    blocks += (params[i].numel() + 2047) / 2048;
+  }
+  Tensor host = at::empty({(int64_t)(rec.size() * sizeof(CastRecord))}, at::TensorOptions().dtype(at::kByte));
+  memcpy(host.data_ptr(), rec.data(), rec.size() * sizeof(CastRecord));
+  return std::make_tuple(host.to(params[0].device()), (int64_t)rec.size(), (int64_t)blocks);
+}
+void run_cast_plan(Tensor plan, int64_t n_items, int64_t total_blocks, int64_t dst_code) {
+  B2PC_GUARD(plan);
+  check(b2pc_multi_cast(plan.data_ptr(), (int)n_items, total_blocks, (int)dst_code, cur_stream()), "multi_cast");
+}
 
 // ---- stochastic depth + residual ----------------------------------------------------------------------------------------------------------
 struct DropPathAddFn : public torch::autograd::Function<DropPathAddFn> {
   static Tensor forward(AutogradContext* ctx, Tensor shortcut, Tensor x, double keep) {
-    need_cuda(x);
+    B2PC_GUARD(x);
     shortcut = shortcut.contiguous();
     x = x.contiguous();
     const int64_t n = x.size(0), c = x.size(1);
@@ -303,6 +455,7 @@ struct DropPathAddFn : public torch::autograd::Function<DropPathAddFn> {
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     Tensor rs = ctx->get_saved_variables()[0];
+    B2PC_GUARD(rs);
     Tensor dy = grads[0].contiguous();
     const int64_t n = dy.size(0), c = dy.size(1);
     const auto xd = (at::ScalarType)ctx->saved_data["xd"].toInt();
@@ -323,12 +476,23 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("patch_attention", [](Tensor qkv, Tensor cu, int64_t max_seqlen, double scale, int64_t impl) {
     return PatchAttentionFn::apply(qkv, cu, max_seqlen, scale, impl);
   });
-  m.def("sparse_conv", [](Tensor feat, Tensor weight, c10::optional<Tensor> bias, Tensor tf, Tensor tb, bool flip, int64_t impl) {
-    return SparseConvFn::apply(feat, weight, bias, tf, tb, flip, impl);
-  });
+  m.def("sparse_conv", [](Tensor feat, Tensor weight, c10::optional<Tensor> bias, Tensor tf, Tensor tb, bool flip, int64_t impl,
+                          c10::optional<Tensor> w16, c10::optional<Tensor> b16) {
+    return SparseConvFn::apply(feat, weight, bias, tf, tb, flip, impl, w16, b16);
+  }, py::arg("feat"), py::arg("weight"), py::arg("bias"), py::arg("table_fwd"), py::arg("table_bwd"), py::arg("flip"), py::arg("impl"),
+     py::arg("w16") = py::none(), py::arg("b16") = py::none());
   m.def("segment_max", [](Tensor x, Tensor order, Tensor start, Tensor len) { return SegmentMaxFn::apply(x, order, start, len); });
   m.def("unpool_add", [](Tensor p, Tensor c, Tensor cl, Tensor order, Tensor len) { return UnpoolAddFn::apply(p, c, cl, order, len); });
-  m.def("linear", [](Tensor x, Tensor w, c10::optional<Tensor> b, int64_t ccode) { return LinearFn::apply(x, w, b, ccode); });
+  m.def("linear", [](Tensor x, Tensor w, c10::optional<Tensor> b, int64_t ccode, c10::optional<Tensor> w16, c10::optional<Tensor> b16) {
+    return LinearFn::apply(x, w, b, ccode, w16, b16);
+  }, py::arg("x"), py::arg("weight"), py::arg("bias"), py::arg("ccode"), py::arg("w16") = py::none(), py::arg("b16") = py::none());
+  m.def("fused_residual", [](Tensor shortcut, Tensor x, c10::optional<Tensor> u, double keep, c10::optional<Tensor> ga, c10::optional<Tensor> ba,
+                             double eps_a, c10::optional<Tensor> gb, c10::optional<Tensor> bb, double eps_b, bool emit_half) {
+    return FusedResidualFn::apply(shortcut, x, u, keep, ga, ba, eps_a, gb, bb, eps_b, emit_half);
+  });
+  m.def("gelu", [](Tensor x) { return GeluFn::apply(x); });
+  m.def("make_cast_plan", &make_cast_plan);
+  m.def("run_cast_plan", &run_cast_plan);
   m.def("drop_path_add", [](Tensor s, Tensor x, double keep) { return DropPathAddFn::apply(s, x, keep); });
   m.def("launch_count", []() { return (int64_t)b2pc_launch_count(); });
 }

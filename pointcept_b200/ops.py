@@ -323,10 +323,10 @@ class SparseConvFn(torch.autograd.Function):
         return dfeat, dweight, dbias, None, None, None
 
 
-def sparse_conv(feat, weight, bias, table_fwd, table_bwd, flip_bwd):
+def sparse_conv(feat, weight, bias, table_fwd, table_bwd, flip_bwd, w16=None, b16=None):
     B = binding()
     if B is not None and feat.dtype in _DTYPES:
-        return B.sparse_conv(feat, weight, bias, table_fwd, table_bwd, bool(flip_bwd), _impl)
+        return B.sparse_conv(feat, weight, bias, table_fwd, table_bwd, bool(flip_bwd), _impl, w16, b16)
     return SparseConvFn.apply(feat, weight, bias, table_fwd, table_bwd, flip_bwd)
 
 
@@ -507,15 +507,114 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def linear(x, weight, bias):
-    """F.linear for 2-D CUDA inputs with the fused bias gradient; falls back to F.linear otherwise."""
+def linear(x, weight, bias, w16=None, b16=None):
+    """F.linear for 2-D CUDA inputs with the fused bias gradient; falls back to F.linear otherwise.
+    w16 / b16: up-to-date half-precision shadows of weight / bias (HalfShadows); they spare the per-call cast kernels."""
     if x.is_cuda and x.dim() == 2 and weight.shape[0] % 4 == 0 and x.dtype in _DTYPES:
         cdtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         B = binding()
         if B is not None:
-            return B.linear(x, weight, bias, _DTYPES[cdtype])
+            return B.linear(x, weight, bias, _DTYPES[cdtype], w16, b16)
         return LinearFn.apply(x, weight, bias, cdtype)
     return torch.nn.functional.linear(x, weight, bias)
+
+
+def fused_residual(shortcut, x, u=None, keep=1.0, ln_a=None, ln_b=None, emit_half=False):
+    """csrc/fused.cuh through the compiled binding: r = shortcut + dropscale * [LN_a](x); optional half copy of r; optional
+    y = LN_b(r) in x's dtype.  ln_a / ln_b: nn.LayerNorm modules or None.  Returns (r, r16 or None, y or None)."""
+    B = binding()
+    assert B is not None, "fused_residual needs the compiled binding"
+    outs = B.fused_residual(shortcut, x, u, float(keep),
+                            None if ln_a is None else ln_a.weight, None if ln_a is None else ln_a.bias, 1e-5 if ln_a is None else ln_a.eps,
+                            None if ln_b is None else ln_b.weight, None if ln_b is None else ln_b.bias, 1e-5 if ln_b is None else ln_b.eps,
+                            bool(emit_half))
+    r = outs[0]
+    r16 = outs[1] if emit_half else None
+    y = outs[-1] if ln_b is not None else None
+    return r, r16, y
+
+
+def fused_residual_supported(x, c):
+    return binding() is not None and x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and c in (32, 64, 128, 256, 512)
+
+
+def gelu(x):
+    """exact (erf) GELU, one kernel per direction through the compiled binding; torch otherwise."""
+    B = binding()
+    if B is not None and x.is_cuda and x.dtype in _DTYPES and x.numel() % 4 == 0:
+        return B.gelu(x)
+    return torch.nn.functional.gelu(x)
+
+
+class HalfShadows:
+    """Half-precision shadows of the fp32 parameters that feed GEMM-shaped kernels (Linear and sparse-conv weights / biases).
+    autocast re-casts every weight on every forward with one kernel each (~250 launches per PT-v3 step); here ONE launch
+    (b2pc_multi_cast) refreshes all shadows whenever a parameter changed (optimizer step, load_state_dict), detected through the
+    tensors' version counters.  Modules read ``_w16`` / ``_b16`` only while ``_w16_ver`` matches the parameter's version."""
+
+    def __init__(self, model):
+        self.model = model
+        self._key = None
+        self._ver = None
+        self._plan = None
+        self._mods = None
+
+    def _modules(self):
+        if self._mods is None:
+            self._mods = [m for m in self.model.modules() if getattr(m, "_b2pc_half_shadow", False)]
+        return self._mods
+
+    @torch.no_grad()
+    def sync(self, dtype):
+        B = binding()
+        if B is None:
+            return
+        mods = self._modules()
+        params = []
+        for m in mods:
+            params.append(m.weight)
+            if m.bias is not None:
+                params.append(m.bias)
+        if not params or not params[0].is_cuda or any(p.dtype != torch.float32 for p in params):
+            return
+        key = (dtype, params[0].device, tuple(p.data_ptr() for p in params))
+        if key != self._key:
+            total = sum((p.numel() + 7) // 8 * 8 for p in params)
+            flat = torch.empty(total, dtype=dtype, device=params[0].device)
+            shadows, off = [], 0
+            for p in params:
+                shadows.append(flat[off:off + p.numel()].view(p.shape))
+                off += (p.numel() + 7) // 8 * 8
+            i = 0
+            for m in mods:
+                m._w16 = shadows[i]
+                i += 1
+                if m.bias is not None:
+                    m._b16 = shadows[i]
+                    i += 1
+                else:
+                    m._b16 = None
+            self._plan = B.make_cast_plan([p.detach() for p in params], shadows)
+            self._key, self._ver = key, None
+            self._flat = flat
+        ver = sum(p._version for p in params)
+        if ver != self._ver:
+            B.run_cast_plan(self._plan[0], self._plan[1], self._plan[2], _DTYPES[dtype])
+            self._ver = ver
+            for m in mods:
+                m._w16_ver = m.weight._version
+                m._b16_ver = m.bias._version if m.bias is not None else -1
+
+
+def shadow_of(module, dtype):
+    """(w16, b16) of a module managed by HalfShadows if they are current for `dtype`, else (None, None)."""
+    w16 = getattr(module, "_w16", None)
+    if w16 is None or w16.dtype != dtype or getattr(module, "_w16_ver", -2) != module.weight._version:
+        return None, None
+    b16 = getattr(module, "_b16", None)
+    if module.bias is not None and (b16 is None or getattr(module, "_b16_ver", -2) != module.bias._version):
+        return None, None
+    return w16, b16
 
 
 def drop_path_add(shortcut, x, drop_prob, training):

@@ -54,13 +54,17 @@ class FusedLinear(nn.Linear):
     kernel saves (measured 48.7 -> 56.5 ms per step), so by default it is used only through the compiled binding."""
 
     use_fused_bias_grad = None   # None: on exactly when the compiled binding is present (its C++ node is cheaper than autograd's)
+    _b2pc_half_shadow = True     # ops.HalfShadows keeps half-precision copies of weight / bias for the autocast path
 
     def forward(self, x):
         on = FusedLinear.use_fused_bias_grad
         if on is None:
             on = ops.binding() is not None
         if on:
-            return ops.linear(x, self.weight, self.bias)
+            w16 = b16 = None
+            if torch.is_autocast_enabled():
+                w16, b16 = ops.shadow_of(self, torch.get_autocast_dtype("cuda"))
+            return ops.linear(x, self.weight, self.bias, w16, b16)
         return nn.functional.linear(x, self.weight, self.bias)
 
 
@@ -192,7 +196,9 @@ class MLP(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        h = self.fc1(x)
+        h = ops.gelu(h) if (type(self.act) is nn.GELU and self.act.approximate == "none") else self.act(h)
+        return self.drop(self.fc2(self.drop(h)))
 
 
 class Block(PointModule):
@@ -222,7 +228,51 @@ class Block(PointModule):
                 if isinstance(seq[0], FusedLayerNorm):
                     seq[0].emit_autocast_dtype = True
 
+    fused = True   # class switch: one fused residual kernel per sub-layer (csrc/fused.cuh) when the compiled binding is present
+
+    def _drop_rand(self, point, n, dev):
+        """uniform randoms for DropPath (one per row), sliced from a pool filled by a single torch.rand per forward"""
+        dp = self.drop_path[0]
+        prob = dp.drop_prob if isinstance(dp, DropPath) else 0.0
+        if prob == 0.0 or not self.training:
+            return None, 1.0
+        pool = point.get("_dp_pool")
+        if pool is None or pool[1] + n > pool[0].numel() or pool[0].device != dev:
+            pool = [torch.rand(max(8 * n, 1 << 20), device=dev), 0]
+            point["_dp_pool"] = pool
+        u = pool[0][pool[1]:pool[1] + n]
+        pool[1] += n
+        return u, 1.0 - prob
+
+    def _forward_fused(self, point):
+        """Same math as forward() below, pre-norm only: CPE(conv -> Linear) -> [LN + residual + LN] -> attention ->
+        [DropPath + residual + LN] -> MLP -> [DropPath + residual (+ half copy for the next conv)]: 3 glue kernels per block."""
+        ln = FusedLayerNorm
+        amp = torch.is_autocast_enabled()
+        r0 = point.feat
+        if r0.dtype != torch.float32:
+            r0 = r0.float()
+        n, dev = r0.shape[0], r0.device
+        sct = self.cpe[0](point.sparse_conv_feat)
+        lin = self.cpe[1](sct.features)
+        r1, _, y1 = ops.fused_residual(r0, lin, None, 1.0, self.cpe[2], self.norm1[0], False)
+        point.feat = y1
+        point = self.attn(point)
+        u, keep = self._drop_rand(point, n, dev)
+        r2, _, y2 = ops.fused_residual(r1, point.feat, u, keep, None, self.norm2[0], False)
+        m = self.mlp[0](y2)
+        u, keep = self._drop_rand(point, n, dev)
+        r3, r16, _ = ops.fused_residual(r2, m, u, keep, None, None, amp and m.dtype != torch.float32)
+        point.feat = r3
+        point.sparse_conv_feat = sct.replace_feature(r3)
+        if r16 is not None:
+            point.sparse_conv_feat._features_half = r16
+        return point
+
     def forward(self, point):
+        if (Block.fused and self.pre_norm and isinstance(self.cpe[2], FusedLayerNorm) and isinstance(self.norm1[0], FusedLayerNorm)
+                and isinstance(self.norm2[0], FusedLayerNorm) and ops.fused_residual_supported(point.feat, self.channels)):
+            return self._forward_fused(point)
         shortcut = point.feat
         point = self.cpe(point)
         point.feat = shortcut + point.feat
@@ -327,7 +377,7 @@ class SerializedPooling(PointModule):
                   "offset_host", "grid_max_host"):
             if k in pl:
                 point_dict[k] = pl[k]
-        for k in ("condition", "context"):
+        for k in ("condition", "context", "_dp_pool"):
             if k in point:
                 point_dict[k] = point[k]
         if self.traceable:
@@ -474,8 +524,30 @@ class PointTransformerV3(PointModule):
         point["_prepared"] = True
         return point
 
+    def _sync_half_shadows(self):
+        """autocast path: refresh the half-precision shadows of every Linear / sparse-conv parameter with one launch"""
+        if not torch.is_autocast_enabled() or ops.binding() is None:
+            return
+        sh = self.__dict__.get("_half_shadows")
+        if sh is None:
+            sh = ops.HalfShadows(self)
+            self.__dict__["_half_shadows"] = sh
+        sh.sync(torch.get_autocast_dtype("cuda"))
+
     def forward(self, data_dict):
         point = data_dict if isinstance(data_dict, Point) and data_dict.get("_prepared", False) else self.prepare(data_dict)
+        self._sync_half_shadows()
+        if "_has_dp" not in self.__dict__:
+            self.__dict__["_has_dp"] = any(isinstance(m, DropPath) and m.drop_prob > 0.0 for m in self.modules())
+        if self.training and self.__dict__["_has_dp"] and Block.fused and ops.binding() is not None:
+            # one torch.rand for every DropPath decision of this forward (two per block, one per row)
+            sizes = [point.host_offset()[-1]] + [pl["offset_host"][-1] for pl in point["_pool_plans"]]
+            need = 0
+            for st in range(self.num_stages):
+                need += 2 * sizes[st] * len([m for m in getattr(self.enc, f"enc{st}").children() if isinstance(m, Block)])
+                if not self.enc_mode and st < self.num_stages - 1:
+                    need += 2 * sizes[st] * len([m for m in getattr(self.dec, f"dec{st}").children() if isinstance(m, Block)])
+            point["_dp_pool"] = [torch.rand(max(need, 1), device=point.feat.device), 0]
         restore = point.get("spatial_restore")
         if restore is not None:
             point.feat = point.feat[point["spatial_perm"]]

@@ -19,6 +19,8 @@ def _triple(v, ndim=3):
 
 
 class SparseConvolution(SparseModule):
+    _b2pc_half_shadow = True     # ops.HalfShadows keeps half-precision copies of weight / bias for the autocast path
+
     def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
                  bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None,
                  algo=None, fp32_accum=None, record_voxel_count=False, act_type=None, act_alpha=0, act_beta=0,
@@ -37,6 +39,9 @@ class SparseConvolution(SparseModule):
         self.padding = _triple(padding)
         self.dilation = _triple(dilation)
         self.output_padding = _triple(output_padding)
+        if subm and any(k % 2 == 0 for k in self.kernel_size):
+            # the backward-data pass reads the forward rulebook with flipped offsets, valid only for symmetric (odd) kernels
+            raise NotImplementedError("SubMConv3d with an even kernel size is not supported (no stock Pointcept config uses one)")
         self.conv1x1 = all(k == 1 for k in self.kernel_size)
         self.subm, self.inverse, self.transposed = subm, inverse, transposed
         self.groups = groups
@@ -100,14 +105,21 @@ class SparseConvolution(SparseModule):
     def forward(self, x):
         assert isinstance(x, SparseConvTensor)
         feat = x.features
+        w16 = b16 = None
         if torch.is_autocast_enabled():
-            feat = feat.to(torch.get_autocast_dtype("cuda"))
+            adt = torch.get_autocast_dtype("cuda")
+            half = getattr(x, "_features_half", None)     # emitted by the producer of x.features (fused residual kernel)
+            feat = half if (half is not None and half.dtype == adt and half.shape == feat.shape) else feat.to(adt)
+            w16, b16 = ops.shadow_of(self, adt)
         kv = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
         w = self.weight.view(self.out_channels, kv, self.in_channels)
         if self.conv1x1 and self.subm:
             # K = 1: plain features @ W^T + b (library GEMM); no rulebook needed
-            out = torch.nn.functional.linear(feat, w[:, 0, :].to(feat.dtype),
-                                             self.bias.to(feat.dtype) if self.bias is not None else None)
+            if w16 is not None:
+                out = ops.linear(feat, w[:, 0, :], self.bias, w16.view(self.out_channels, self.in_channels), b16)
+            else:
+                out = torch.nn.functional.linear(feat, w[:, 0, :].to(feat.dtype),
+                                                 self.bias.to(feat.dtype) if self.bias is not None else None)
             return x.replace_feature(out)
         data = self._rulebook(x)
         if self.in_channels % 16 != 0 and feat.dtype in (torch.float16, torch.bfloat16):
@@ -116,15 +128,16 @@ class SparseConvolution(SparseModule):
             padc = 16 - self.in_channels % 16
             feat = torch.nn.functional.pad(feat, (0, padc))
             w = torch.nn.functional.pad(w, (0, padc))
+            w16 = b16 = None
         if self.inverse:
-            out = ops.sparse_conv(feat, w, self.bias, data.pair_bwd, data.pair_fwd, False)
+            out = ops.sparse_conv(feat, w, self.bias, data.pair_bwd, data.pair_fwd, False, w16, b16)
             res = SparseConvTensor(out, data.indices, data.spatial_shape, x.batch_size, x.grid, x.voxel_num,
                                    x.indice_dict, x.benchmark)
         elif self.subm:
-            out = ops.sparse_conv(feat, w, self.bias, data.pair_fwd, data.pair_fwd, True)
+            out = ops.sparse_conv(feat, w, self.bias, data.pair_fwd, data.pair_fwd, True, w16, b16)
             res = x.replace_feature(out)
         else:
-            out = ops.sparse_conv(feat, w, self.bias, data.pair_fwd, data.pair_bwd, False)
+            out = ops.sparse_conv(feat, w, self.bias, data.pair_fwd, data.pair_bwd, False, w16, b16)
             res = SparseConvTensor(out, data.out_indices, data.out_spatial_shape, x.batch_size, x.grid, x.voxel_num,
                                    x.indice_dict, x.benchmark)
         res.benchmark_record = x.benchmark_record

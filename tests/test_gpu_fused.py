@@ -1,0 +1,171 @@
+"""Fused residual glue (csrc/fused.cuh), the half-precision parameter shadows and the GELU kernels against their plain-torch
+composition (the ops the reference block runs one by one, ptv3m1:318-338)."""
+import pytest
+import torch
+import torch.nn as nn
+
+from pointcept_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+def _need_binding():
+    if _lib.torch_binding() is None:
+        pytest.skip("compiled binding not built")
+
+
+@pytest.mark.parametrize("c", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("use_a,use_b,use_u,half", [(True, True, False, False), (False, True, True, False), (False, False, True, True),
+                                                    (True, False, False, True), (False, False, False, False)])
+def test_fused_residual_matches_torch_composition(c, dtype, use_a, use_b, use_u, half):
+    _need_binding()
+    torch.manual_seed(c)
+    n, keep = 2777, 0.7
+    shortcut = torch.randn(n, c, device=DEV)
+    x = (torch.randn(n, c, device=DEV) * 1.5 + 0.3).to(dtype)
+    ln_a = nn.LayerNorm(c).to(DEV) if use_a else None
+    ln_b = nn.LayerNorm(c).to(DEV) if use_b else None
+    for ln in (ln_a, ln_b):
+        if ln is not None:
+            with torch.no_grad():
+                ln.weight.normal_(1.0, 0.3)
+                ln.bias.normal_(0.0, 0.3)
+    u = torch.rand(n, device=DEV) if use_u else None
+    emit = half and dtype != torch.float32
+    s1, x1 = shortcut.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    r, r16, y = ops.fused_residual(s1, x1, u, keep, ln_a, ln_b, emit)
+    # reference composition in fp64 on identically rounded inputs
+    s2, x2 = shortcut.double().requires_grad_(True), x.double().requires_grad_(True)
+    pa = [p.detach().double().requires_grad_(True) for p in (ln_a.weight, ln_a.bias)] if use_a else None
+    pb = [p.detach().double().requires_grad_(True) for p in (ln_b.weight, ln_b.bias)] if use_b else None
+    t = x2
+    if use_a:
+        t = torch.nn.functional.layer_norm(t, (c,), pa[0], pa[1], 1e-5)
+    if use_u:
+        t = t * ((u < keep).double() / keep)[:, None]
+    r_ref = s2 + t
+    y_ref = torch.nn.functional.layer_norm(r_ref, (c,), pb[0], pb[1], 1e-5) if use_b else None
+    assert r.dtype == torch.float32 and rel_l2(r, r_ref) < 1e-6
+    tol = 1e-6 if dtype == torch.float32 else (4e-3 if dtype == torch.bfloat16 else 5e-4)
+    if emit:
+        assert r16.dtype == dtype and torch.equal(r16, r.to(dtype))
+    if use_b:
+        assert y.dtype == dtype and rel_l2(y, y_ref) < tol
+    # backward: every output that exists gets an upstream gradient
+    gr = torch.randn(n, c, device=DEV)
+    g16 = torch.randn(n, c, device=DEV).to(dtype) if emit else None
+    gy = torch.randn(n, c, device=DEV).to(dtype) if use_b else None
+    outs, gs = [r], [gr]
+    loss_ref = (r_ref * gr.double()).sum()
+    if emit:
+        outs.append(r16); gs.append(g16)
+        loss_ref = loss_ref + (r_ref * g16.double()).sum()
+    if use_b:
+        outs.append(y); gs.append(gy)
+        loss_ref = loss_ref + (y_ref * gy.double()).sum()
+    torch.autograd.backward(outs, gs)
+    loss_ref.backward()
+    assert rel_l2(s1.grad, s2.grad) < 1e-5
+    assert rel_l2(x1.grad.float(), x2.grad) < (1e-5 if dtype == torch.float32 else (6e-3 if dtype == torch.bfloat16 else 8e-4))
+    if use_a:
+        assert rel_l2(ln_a.weight.grad, pa[0].grad) < 1e-4 and rel_l2(ln_a.bias.grad, pa[1].grad) < 1e-4
+    if use_b:
+        assert rel_l2(ln_b.weight.grad, pb[0].grad) < 1e-4 and rel_l2(ln_b.bias.grad, pb[1].grad) < 1e-4
+
+
+def test_half_shadows_follow_parameter_updates_with_one_launch():
+    _need_binding()
+    from pointcept_b200.ptv3 import FusedLinear
+    from pointcept_b200.spconv import pytorch as spconv
+    torch.manual_seed(0)
+    model = nn.Sequential(FusedLinear(32, 96), FusedLinear(96, 32, bias=False), spconv.SubMConv3d(32, 32, 3, indice_key="k")).to(DEV)
+    sh = ops.HalfShadows(model)
+    L = _lib.lib()
+    c0 = L.b2pc_launch_count()
+    sh.sync(torch.bfloat16)
+    assert L.b2pc_launch_count() - c0 == 1
+    for m in model:
+        w16, b16 = ops.shadow_of(m, torch.bfloat16)
+        assert w16 is not None and torch.equal(w16, m.weight.detach().bfloat16())
+        if m.bias is not None:
+            assert torch.equal(b16, m.bias.detach().bfloat16())
+    c0 = L.b2pc_launch_count()
+    sh.sync(torch.bfloat16)                      # nothing changed: no launch
+    assert L.b2pc_launch_count() == c0
+    with torch.no_grad():
+        model[0].weight.add_(1.0)                # an optimizer step bumps the version counter
+    assert ops.shadow_of(model[0], torch.bfloat16) == (None, None)      # stale shadows are never handed out
+    sh.sync(torch.bfloat16)
+    assert torch.equal(ops.shadow_of(model[0], torch.bfloat16)[0], model[0].weight.detach().bfloat16())
+    # Linear through the shadows == autocast F.linear, and the weight gradient arrives in fp32 without a bf16 round trip
+    x = torch.randn(1000, 32, device=DEV, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = model[0](x)
+        y_ref = torch.nn.functional.linear(x, model[0].weight, model[0].bias)
+    assert torch.equal(y, y_ref)
+    y.float().square().sum().backward()
+    g = model[0].weight.grad
+    dy = (2 * y.detach().float()).bfloat16()
+    want = dy.double().t() @ x.detach().bfloat16().double()
+    assert g.dtype == torch.float32 and rel_l2(g, want) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_gelu_kernels_match_torch_exact_gelu(dtype):
+    _need_binding()
+    torch.manual_seed(0)
+    x = (torch.randn(5000, 128, device=DEV) * 2).to(dtype).requires_grad_(True)
+    y = ops.gelu(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    x2 = x.detach().double().requires_grad_(True)
+    y2 = torch.nn.functional.gelu(x2)
+    y2.backward(dy.double())
+    tol = 1e-6 if dtype == torch.float32 else (4e-3 if dtype == torch.bfloat16 else 5e-4)
+    assert rel_l2(y.detach(), y2.detach()) < tol and rel_l2(x.grad, x2.grad) < tol
+
+
+def test_fused_block_path_matches_unfused_block_path():
+    """One PT-v3 Block (ptv3m1:251-338) forward + backward: the fused-glue path against the op-by-op path of the same module, fp32
+    (identical rounding points) at 1e-5, and under bf16 autocast at bf16 noise level."""
+    _need_binding()
+    import numpy as np
+    from pointcept_b200 import synth
+    from pointcept_b200.ptv3 import Block
+    from pointcept_b200.structure import Point
+    torch.manual_seed(0)
+    b = synth.make_batch(2, seed=3, target_voxels=1500)
+    blk = Block(64, 4, patch_size=128, drop_path=0.0, norm_layer=__import__("pointcept_b200.ptv3", fromlist=["x"]).FusedLayerNorm,
+                cpe_indice_key="s0").to(DEV).train()
+
+    def run(fused, amp):
+        Block.fused = fused
+        try:
+            p = Point(coord=torch.from_numpy(b["coord"]).to(DEV), grid_coord=torch.from_numpy(b["grid_coord"]).to(DEV),
+                      offset=torch.from_numpy(b["offset"]).to(DEV), feat=torch.randn(len(b["coord"]), 64, device=DEV,
+                                                                                    generator=torch.Generator(DEV).manual_seed(1)))
+            p.feat.requires_grad_(True)
+            x0 = p.feat
+            p.serialization(order=["z", "hilbert"])
+            p.sparsify()
+            blk.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                out = blk(p).feat
+            out.float().square().mean().backward()
+            return out.detach().float(), x0.grad.clone(), {k: v.grad.clone() for k, v in blk.named_parameters()}
+        finally:
+            Block.fused = True
+
+    for amp, tol in ((False, 2e-5), (True, 2e-2)):
+        o1, g1, p1 = run(True, amp)
+        o0, g0, p0 = run(False, amp)
+        assert rel_l2(o1, o0) < tol and rel_l2(g1, g0) < tol * 2
+        for k in p0:
+            assert rel_l2(p1[k], p0[k]) < tol * 5, k

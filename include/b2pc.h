@@ -186,6 +186,25 @@ int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* wo
 
 
 /* ---------------------------------------------------------------------------------------------
+ * Serialized attention = patch attention with the reference's [order] gather and [inverse] gather fused in
+ * (SerializedAttention.forward, point_transformer_v3m1_base.py:184-216): qkv_points [N, 3, H, D] and out_points [N, H, D]
+ * are in POINT order; slot t of the padded patch sequence (T_pad slots, sequences given by cu_seqlens) reads point row
+ * gidx[t] = order[pad][t]; sidx[t] = that point row when t is the point's primary slot (inverse = unpad[inverse_order]),
+ * and -(r+1) when t is the r-th borrowed filler slot (its output is dropped, :216).  dup_point[r] = the point of filler r.
+ * lse [H, T_pad].  Tensor-core path only (head_dim 16, fp16 / bf16): B2PC_ERR_UNSUPPORTED otherwise (callers then run the
+ * unfused sequence gather -> b2pc_patch_attn_* -> gather).
+ * ------------------------------------------------------------------------------------------- */
+int b2pc_serialized_attn_fwd(const void* qkv_points, int dtype, const int32_t* gidx, const int32_t* sidx,
+                             const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t_pad, int heads,
+                             int head_dim, float scale, void* out_points, float* lse, b2pc_stream_t stream);
+size_t b2pc_serialized_attn_bwd_workspace_bytes(int64_t t_pad, int heads, int head_dim, int64_t n_dup);
+int b2pc_serialized_attn_bwd(const void* dout_points, const void* qkv_points, const void* out_points, const float* lse,
+                             int dtype, const int32_t* gidx, const int32_t* sidx, const int32_t* dup_point,
+                             int64_t n_dup, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t_pad,
+                             int heads, int head_dim, float scale, void* dqkv_points, void* workspace,
+                             size_t workspace_bytes, b2pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused residual glue of one PT-v3 block (point_transformer_v3m1_base.py:318-338):
  *     t = x;  t = LayerNorm_a(t) [gamma_a != NULL];  t *= (u[row] < keep ? 1/keep : 0) [u != NULL, DropPath :313-315]
  *     r = shortcut + t (fp32, written);  r16 = (dtype) r [r16 != NULL];  y = LayerNorm_b(r) in dtype [gamma_b != NULL]

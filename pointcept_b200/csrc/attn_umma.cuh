@@ -39,11 +39,16 @@ template <int BN> __host__ __device__ constexpr int attn_tmem_cols() { return BN
 template <int BN> __host__ __device__ constexpr int attn_fwd_smem_bytes() { return kAuQ * 32 + kAuStages * BN * 64 + 128; }
 
 // TMA = true: Q / K / V tiles arrive by cp.async.bulk.tensor (one elected thread, byte-counted mbarriers); false: cp.async.
-template <typename T, int BN, bool TMA>
+// GATHER = true (serialized attention, ptv3m1:188,216 fused in): qkv holds POINT rows [N, 3, H, 16]; slot t of the padded patch
+// sequence reads point row gidx[t] (= order[pad][t]) and writes its output to point row sidx[t] when sidx[t] >= 0 (the slot is
+// the point's primary slot; borrowed filler slots have sidx < 0 and are dropped) -- the [order] gather and the [inverse]
+// gather of the reference happen inside the tile loads / the epilogue and the padded qkv / out tensors never exist.
+template <typename T, int BN, bool TMA, bool GATHER>
 __global__ void __launch_bounds__(kAuQ)
 attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, int64_t t_total, int H, float scale,
                      T* __restrict__ out, float* __restrict__ lse, AttnDesc dd, const __grid_constant__ CUtensorMap tmap_q,
-                     const __grid_constant__ CUtensorMap tmap_kv) {
+                     const __grid_constant__ CUtensorMap tmap_kv, const int32_t* __restrict__ gidx, const int32_t* __restrict__ sidx) {
+  static_assert(!(TMA && GATHER), "gathered rows are fetched with cp.async");
   using namespace umma;
   constexpr int D = 16;
   constexpr int TMEM_COLS = attn_tmem_cols<BN>();
@@ -64,6 +69,10 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
   if (q0 >= len) return;
   const int nblk = (len + BN - 1) / BN;
   const int64_t row_stride = (int64_t)3 * H * D;  // elements between consecutive tokens
+  // Bulk tile loads fetch whole BN-row boxes: past the end of a ragged sequence they would bring in rows of the NEXT sequence,
+  // and although their probabilities are zeroed, 0 x Inf/NaN in the PV product is not -- so ragged sequences take the
+  // zero-filling cp.async path (per CTA decision; full patches, i.e. nearly all of them, take TMA).
+  const bool tma = TMA && (len % BN == 0);
 
   if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   if (tid == 0) {
@@ -72,8 +81,6 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     mbar_init(qbar, 1);
     fence_mbar_init();
   }
-  // TMA: rows past the end of the sequence are whatever follows in the packed tensor (or zeros past T); they only ever
-  // meet masked score columns / zero probabilities, exactly like the zero-filled rows of the cp.async path.
   auto tma_kv = [&](int blk, int stage) {
     uint8_t* ks = kv_s + stage * BN * 64;
     const int row = (int)(s0 + blk * BN);
@@ -85,10 +92,12 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
   };
 
   // ---- loads: 16-byte pieces into "plane" layout: piece (row r, chunk c) -> c * rows*16 + r*16 ----------------------
-  const T* base_q = qkv + (s0 * 3 + 0) * H * D + h * D;
-  const T* base_k = qkv + (s0 * 3 + 1) * H * D + h * D;
-  const T* base_v = qkv + (s0 * 3 + 2) * H * D + h * D;
-  if (TMA) {
+  const int64_t row_base = GATHER ? 0 : s0;   // GATHER: rows are addressed through gidx
+  const T* base_q = qkv + (row_base * 3 + 0) * H * D + h * D;
+  const T* base_k = qkv + (row_base * 3 + 1) * H * D + h * D;
+  const T* base_v = qkv + (row_base * 3 + 2) * H * D + h * D;
+  const int32_t* gix = GATHER ? gidx + s0 : nullptr;
+  if (tma) {
     if (tid == 0) {
       mbar_expect_tx(qbar, kAuQ * 32);
       tma_load_2d(smem_u32(q_s), &tmap_q, h * D, (int)(s0 + q0), qbar);
@@ -99,7 +108,8 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
   } else {
     const int r = tid;
     const bool ok = q0 + r < len;
-    const T* src = base_q + (int64_t)(q0 + r) * row_stride;
+    const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(gix + q0 + r) : 0) : (int64_t)(q0 + r);
+    const T* src = base_q + prow * row_stride;
     cp_async16(smem_u32(q_s + r * 16), ok ? src : base_q, ok);
     cp_async16(smem_u32(q_s + kAuQ * 16 + r * 16), ok ? src + 8 : base_q, ok);
   }
@@ -110,11 +120,12 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     for (int p = tid; p < 4 * BN; p += kAuQ) {
       const int which = p / (2 * BN), rem = p % (2 * BN), r = rem >> 1, c = rem & 1;
       const bool ok = k0 + r < len;
-      const T* src = (which ? base_v : base_k) + (int64_t)(k0 + r) * row_stride + c * 8;
+      const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(gix + k0 + r) : 0) : (int64_t)(k0 + r);
+      const T* src = (which ? base_v : base_k) + prow * row_stride + c * 8;
       cp_async16(smem_u32((which ? vs : ks) + c * BN * 16 + r * 16), ok ? src : base_k, ok);
     }
   };
-  if (!TMA) {
+  if (!tma) {
     load_kv(0, 0);
     cp_async_commit();
     if (nblk > 1) load_kv(1, 1);
@@ -140,13 +151,13 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     const int stage = j % kAuStages;
     uint8_t* ks = kv_s + stage * BN * 64;
     uint8_t* vs = ks + BN * 32;
-    if (!TMA) {
+    if (!tma) {
       cp_async_wait<1>();
       fence_proxy_async();
       __syncthreads();
     }
     if (tid == 0) {
-      if (TMA) {
+      if (tma) {
         if (j == 0) mbar_wait(qbar, 0);
         mbar_wait(&full[stage], (j / kAuStages) & 1);
       }
@@ -157,7 +168,7 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     mbar_wait(bar, j & 1);
     tc_fence_after();
     // S_j is complete, hence so is PV_{j-1}: its K/V stage is free again -> prefetch block j+2 into it
-    if (TMA) {
+    if (tma) {
       if (tid == 0 && j + 2 < nblk) tma_kv(j + 2, (j + 2) % kAuStages);
     } else {
       if (j + 2 < nblk) load_kv(j + 2, (j + 2) % kAuStages);
@@ -256,9 +267,12 @@ attn_fwd_umma_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu, 
     uint32_t w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = pack2<T>(o[2 * i] * inv, o[2 * i + 1] * inv);
-    uint4* dst = reinterpret_cast<uint4*>(out + ((s0 + qi) * H + h) * D);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    const int64_t orow = GATHER ? (int64_t)__ldg(sidx + s0 + qi) : s0 + qi;
+    if (orow >= 0) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (orow * H + h) * D);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
     lse[(int64_t)h * t_total + s0 + qi] = (m + log2f(l)) * kLn2;
   }
   tc_fence_before();
@@ -294,40 +308,48 @@ inline bool attn_use_tma() {
   return v;
 }
 
+// gidx / sidx non-null: serialized (gather-fused) mode, see the kernel comment
 template <typename T, int BN>
 inline int launch_attn_fwd_umma_t(const void* qkv, const int32_t* cu, int n_seq, int max_seqlen, int64_t t, int H, float scale,
-                                  void* out, float* lse, cudaStream_t stream) {
-  static bool configured = false;
+                                  void* out, float* lse, const int32_t* gidx, const int32_t* sidx, cudaStream_t stream) {
   constexpr int smem = attn_fwd_smem_bytes<BN>();
-  if (!configured) {
-    cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = true;
-  }
   dim3 grid((unsigned)ceil_div(max_seqlen, kAuQ), n_seq, H);
   CUtensorMap mq, mkv;
-  const bool bf16 = UmmaFmt<T>::v == umma::kFmtBF16;
-  const bool tma = attn_use_tma() && t < (1ll << 31) && make_plane_tensor_map(&mq, qkv, bf16, (uint64_t)t, (uint64_t)3 * H * 16, kAuQ) &&
-                   make_plane_tensor_map(&mkv, qkv, bf16, (uint64_t)t, (uint64_t)3 * H * 16, BN);
-  if (tma)
-    attn_fwd_umma_kernel<T, BN, true><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN), mq, mkv);
-  else
-    attn_fwd_umma_kernel<T, BN, false><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN), mq, mkv);
+  if (gidx) {
+    cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attn_fwd_umma_kernel<T, BN, false, true><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN), mq, mkv,
+                                                                           gidx, sidx);
+  } else {
+    const bool bf16 = UmmaFmt<T>::v == umma::kFmtBF16;
+    const bool tma = attn_use_tma() && t < (1ll << 31) && make_plane_tensor_map(&mq, qkv, bf16, (uint64_t)t, (uint64_t)3 * H * 16, kAuQ) &&
+                     make_plane_tensor_map(&mkv, qkv, bf16, (uint64_t)t, (uint64_t)3 * H * 16, BN);
+    // the attribute is per device: set it on every launch (a few hundred ns) instead of caching it in a process-wide static
+    if (tma) {
+      cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attn_fwd_umma_kernel<T, BN, true, false><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN), mq, mkv,
+                                                                             nullptr, nullptr);
+    } else {
+      cudaFuncSetAttribute(attn_fwd_umma_kernel<T, BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attn_fwd_umma_kernel<T, BN, false, false><<<grid, kAuQ, smem, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse, attn_desc(BN), mq,
+                                                                              mkv, nullptr, nullptr);
+    }
+  }
   count_launches(1);
   B2PC_CHECK_LAUNCH("patch_attn_fwd(tcgen05)");
   return B2PC_OK;
 }
 
 inline int launch_attn_fwd_umma(const void* qkv, int dtype, const int32_t* cu, int n_seq, int max_seqlen, int64_t t, int H, int D,
-                                float scale, void* out, float* lse, cudaStream_t stream) {
+                                float scale, void* out, float* lse, cudaStream_t stream, const int32_t* gidx = nullptr,
+                                const int32_t* sidx = nullptr) {
   (void)D;
   if (n_seq == 0 || t == 0) return B2PC_OK;
   const int bn = attn_block_n();
   if (dtype == B2PC_BF16)
-    return bn == 64 ? launch_attn_fwd_umma_t<__nv_bfloat16, 64>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, stream)
-                    : launch_attn_fwd_umma_t<__nv_bfloat16, 128>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, stream);
-  return bn == 64 ? launch_attn_fwd_umma_t<__half, 64>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, stream)
-                  : launch_attn_fwd_umma_t<__half, 128>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, stream);
+    return bn == 64 ? launch_attn_fwd_umma_t<__nv_bfloat16, 64>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, gidx, sidx, stream)
+                    : launch_attn_fwd_umma_t<__nv_bfloat16, 128>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, gidx, sidx, stream);
+  return bn == 64 ? launch_attn_fwd_umma_t<__half, 64>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, gidx, sidx, stream)
+                  : launch_attn_fwd_umma_t<__half, 128>(qkv, cu, n_seq, max_seqlen, t, H, scale, out, lse, gidx, sidx, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -351,11 +373,16 @@ constexpr int kAbTmemCols = 256;
 constexpr int kAbStageBytes = 2048 + 2048 + 256 + 256;
 constexpr int kAbSmemBytes = 4096 + 4096 + 16384 + kAbStages * kAbStageBytes + 64;
 
-template <typename T>
+// GATHER = true: serialized mode (see the forward kernel): qkv / dout / dqkv hold POINT rows; slot t reads point row gidx[t],
+// its dO is dout[sidx[t]] when sidx[t] >= 0 and zero otherwise (the output of a borrowed filler slot was dropped); dK / dV of a
+// primary slot go straight to the point's row of dqkv, those of filler slot with sidx = -(r+1) to row r of `side` [n_dup, 2, H, 16]
+// (added to the point's row afterwards: a point owns at most one filler slot besides its primary one).
+template <typename T, bool GATHER>
 __global__ void __launch_bounds__(kAbK)
 attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, const float* __restrict__ lse,
                      const float* __restrict__ delta, const int32_t* __restrict__ cu, int64_t t_total, int H, float scale,
-                     T* __restrict__ dqkv, float* __restrict__ dq_acc) {
+                     T* __restrict__ dqkv, float* __restrict__ dq_acc, const int32_t* __restrict__ gidx,
+                     const int32_t* __restrict__ sidx, T* __restrict__ side) {
   using namespace umma;
   constexpr int D = 16;
   constexpr uint32_t COL_S = 0, COL_DP = 64, COL_P = 128, COL_DS = 160, COL_DV = 192, COL_DK = 208, COL_DQ = 224;
@@ -379,16 +406,20 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   if (warp == 0) { tmem_alloc(tmem_slot, kAbTmemCols); tmem_relinquish(); }
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
 
-  const T* base_q = qkv + (s0 * 3 + 0) * H * D + h * D;
-  const T* base_k = qkv + (s0 * 3 + 1) * H * D + h * D;
-  const T* base_v = qkv + (s0 * 3 + 2) * H * D + h * D;
-  const T* base_do = dout + s0 * H * D + h * D;
+  const int64_t row_base = GATHER ? 0 : s0;
+  const T* base_q = qkv + (row_base * 3 + 0) * H * D + h * D;
+  const T* base_k = qkv + (row_base * 3 + 1) * H * D + h * D;
+  const T* base_v = qkv + (row_base * 3 + 2) * H * D + h * D;
+  const T* base_do = dout + row_base * H * D + h * D;
+  const int32_t* gix = GATHER ? gidx + s0 : nullptr;
+  const int32_t* six = GATHER ? sidx + s0 : nullptr;
   const float* base_lse = lse + (int64_t)h * t_total + s0;
   const float* base_dl = delta + (int64_t)h * t_total + s0;
   {  // K_j, V_j: thread = key row, two 16-byte pieces each, plane layout (chunk c -> c*2048 + row*16)
     const bool ok = k0 + tid < len;
-    const T* ks = base_k + (int64_t)(k0 + tid) * row_stride;
-    const T* vs = base_v + (int64_t)(k0 + tid) * row_stride;
+    const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(gix + k0 + tid) : 0) : (int64_t)(k0 + tid);
+    const T* ks = base_k + prow * row_stride;
+    const T* vs = base_v + prow * row_stride;
     cp_async16(smem_u32(k_s + tid * 16), ok ? ks : base_k, ok);
     cp_async16(smem_u32(k_s + 2048 + tid * 16), ok ? ks + 8 : base_k, ok);
     cp_async16(smem_u32(v_s + tid * 16), ok ? vs : base_k, ok);
@@ -401,13 +432,16 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       const int which = tid >> 6, r = (tid & 63);
       const bool ok = q0 + r < len;
       if (which == 0) {
-        const T* src = base_q + (int64_t)(q0 + r) * row_stride;
+        const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(gix + q0 + r) : 0) : (int64_t)(q0 + r);
+        const T* src = base_q + prow * row_stride;
         cp_async16(smem_u32(st + r * 16), ok ? src : base_q, ok);
         cp_async16(smem_u32(st + 1024 + r * 16), ok ? src + 8 : base_q, ok);
       } else {
-        const T* src = base_do + (int64_t)(q0 + r) * (H * D);
-        cp_async16(smem_u32(st + 2048 + r * 16), ok ? src : base_do, ok);
-        cp_async16(smem_u32(st + 2048 + 1024 + r * 16), ok ? src + 8 : base_do, ok);
+        const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(six + q0 + r) : -1) : (int64_t)(q0 + r);
+        const bool okd = ok && prow >= 0;
+        const T* src = base_do + (okd ? prow : 0) * (H * D);
+        cp_async16(smem_u32(st + 2048 + r * 16), src, okd);
+        cp_async16(smem_u32(st + 2048 + 1024 + r * 16), src + 8, okd);
       }
       // lse / delta of the 64 queries (4-byte async copies; zero when the query does not exist)
       const float* g = (which == 0 ? base_lse : base_dl) + q0 + r;
@@ -545,8 +579,20 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
         wv[e] = pack2<T>(__uint_as_float(rv[2 * e]), __uint_as_float(rv[2 * e + 1]));
         wk[e] = pack2<T>(__uint_as_float(rk[2 * e]) * scale, __uint_as_float(rk[2 * e + 1]) * scale);
       }
-      uint4* dk = reinterpret_cast<uint4*>(dqkv + (((s0 + ki) * 3 + 1) * H + h) * D);
-      uint4* dv = reinterpret_cast<uint4*>(dqkv + (((s0 + ki) * 3 + 2) * H + h) * D);
+      uint4 *dk, *dv;
+      if (GATHER) {
+        const int64_t si = __ldg(six + ki);
+        if (si >= 0) {
+          dk = reinterpret_cast<uint4*>(dqkv + ((si * 3 + 1) * H + h) * D);
+          dv = reinterpret_cast<uint4*>(dqkv + ((si * 3 + 2) * H + h) * D);
+        } else {
+          dk = reinterpret_cast<uint4*>(side + (((-si - 1) * 2 + 0) * H + h) * D);
+          dv = reinterpret_cast<uint4*>(side + (((-si - 1) * 2 + 1) * H + h) * D);
+        }
+      } else {
+        dk = reinterpret_cast<uint4*>(dqkv + (((s0 + ki) * 3 + 1) * H + h) * D);
+        dv = reinterpret_cast<uint4*>(dqkv + (((s0 + ki) * 3 + 2) * H + h) * D);
+      }
       dk[0] = make_uint4(wk[0], wk[1], wk[2], wk[3]);
       dk[1] = make_uint4(wk[4], wk[5], wk[6], wk[7]);
       dv[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
@@ -558,14 +604,19 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   if (warp == 0) tmem_dealloc(tmem_base, kAbTmemCols);
 }
 
-// dqkv[t, 0, h, :] = dq_acc[t, h, :] * scale
+// dqkv[row(t), 0, h, :] = dq_acc[t, h, :] * scale; serialized mode: row(t) = sidx[t] (filler slots have a zero dQ and are skipped)
 template <typename T>
 __global__ void __launch_bounds__(256)
-attn_dq_finish_kernel(const float* __restrict__ dq_acc, int64_t n_rows /* T*H */, int H, float scale, T* __restrict__ dqkv) {
+attn_dq_finish_kernel(const float* __restrict__ dq_acc, int64_t n_rows /* T*H */, int H, float scale, T* __restrict__ dqkv,
+                      const int32_t* __restrict__ sidx) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
-  const int64_t t = i / H;
+  int64_t t = i / H;
   const int h = (int)(i % H);
+  if (sidx) {
+    t = sidx[t];
+    if (t < 0) return;
+  }
   const float4* src = reinterpret_cast<const float4*>(dq_acc + i * 16);
   uint32_t w[8];
 #pragma unroll
@@ -579,69 +630,100 @@ attn_dq_finish_kernel(const float* __restrict__ dq_acc, int64_t n_rows /* T*H */
   dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-inline size_t attn_bwd_umma_workspace_bytes(int64_t t, int H, int D) {
-  (void)D;
-  return 2 * align_up((size_t)t * H * sizeof(float), 256) + align_up((size_t)t * H * 16 * sizeof(float), 256) + 256;
+// serialized mode: dqkv[dup_point[r], 1 + which, h, :] += side[r, which, h, :]   (one thread per (r, which, h), 16 channels)
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_dup_add_kernel(const T* __restrict__ side, const int32_t* __restrict__ dup_point, int64_t n_dup, int H, T* __restrict__ dqkv) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // over n_dup * 2 * H
+  if (i >= n_dup * 2 * H) return;
+  const int h = (int)(i % H);
+  const int which = (int)((i / H) % 2);
+  const int64_t r = i / (2 * H);
+  const T* src = side + i * 16;
+  T* dst = dqkv + (((int64_t)dup_point[r] * 3 + 1 + which) * H + h) * 16;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) dst[e] = from_f32<T>(to_f32(dst[e]) + to_f32(src[e]));
 }
 
-// ndelta[h, t] = -sum_d dout*out,  nlse2[h, t] = -lse[h, t] * log2(e)   (the signs / scale the main kernel's packed FMAs want)
+inline size_t attn_bwd_umma_workspace_bytes(int64_t t, int H, int D, int64_t n_dup = 0) {
+  (void)D;
+  return 2 * align_up((size_t)t * H * sizeof(float), 256) + align_up((size_t)t * H * 16 * sizeof(float), 256) +
+         align_up((size_t)n_dup * 2 * H * 16 * 2, 256) + 256;
+}
+
+// ndelta[h, t] = -sum_d dout*out,  nlse2[h, t] = -lse[h, t] * log2(e)   (the signs / scale the main kernel's packed FMAs want);
+// serialized mode: dout / out are point rows, slot t uses row sidx[t] and gets delta = 0 when it is a filler slot
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const T* __restrict__ dout, const T* __restrict__ out, const float* __restrict__ lse, int64_t t_total, int H,
-                     float* __restrict__ ndelta, float* __restrict__ nlse2) {
+                     float* __restrict__ ndelta, float* __restrict__ nlse2, const int32_t* __restrict__ sidx) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // over T*H, (t, h) order
   if (i >= t_total * H) return;
   const int64_t t = i / H;
   const int h = (int)(i % H);
-  const uint4* a = reinterpret_cast<const uint4*>(dout + i * 16);
-  const uint4* b = reinterpret_cast<const uint4*>(out + i * 16);
   float acc = 0.f;
+  const int64_t row = sidx ? (int64_t)sidx[t] : t;
+  if (row >= 0) {
+    const uint4* a = reinterpret_cast<const uint4*>(dout + (row * H + h) * 16);
+    const uint4* b = reinterpret_cast<const uint4*>(out + (row * H + h) * 16);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint4 va = a[q], vb = b[q];
-    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    for (int q = 0; q < 2; ++q) {
+      const uint4 va = a[q], vb = b[q];
+      const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const T* pa = reinterpret_cast<const T*>(&wa[e]);
-      const T* pb = reinterpret_cast<const T*>(&wb[e]);
-      acc = fmaf(to_f32(pa[0]), to_f32(pb[0]), acc);
-      acc = fmaf(to_f32(pa[1]), to_f32(pb[1]), acc);
+      for (int e = 0; e < 4; ++e) {
+        const T* pa = reinterpret_cast<const T*>(&wa[e]);
+        const T* pb = reinterpret_cast<const T*>(&wb[e]);
+        acc = fmaf(to_f32(pa[0]), to_f32(pb[0]), acc);
+        acc = fmaf(to_f32(pa[1]), to_f32(pb[1]), acc);
+      }
     }
   }
   ndelta[(int64_t)h * t_total + t] = -acc;
   nlse2[(int64_t)h * t_total + t] = -lse[(int64_t)h * t_total + t] * kLog2e;
 }
 
+// gidx non-null: serialized mode (dout / qkv / out / dqkv are point rows; see the kernel comments)
 template <typename T>
 inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void* out, const float* lse, const int32_t* cu, int n_seq,
-                                  int max_seqlen, int64_t t, int H, float scale, void* dqkv, void* ws, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(attn_bwd_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
-    configured = true;
-  }
+                                  int max_seqlen, int64_t t, int H, float scale, void* dqkv, void* ws, cudaStream_t stream,
+                                  const int32_t* gidx, const int32_t* sidx, const int32_t* dup_point, int64_t n_dup) {
   float* delta = (float*)ws;                                                        // holds -delta
   float* nlse2 = (float*)((char*)ws + align_up((size_t)t * H * sizeof(float), 256));  // holds -lse * log2(e)
   float* dq_acc = (float*)((char*)ws + 2 * align_up((size_t)t * H * sizeof(float), 256));
-  attn_bwd_prep_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>((const T*)dout, (const T*)out, lse, t, H, delta, nlse2);
+  T* side = (T*)((char*)dq_acc + align_up((size_t)t * H * 16 * sizeof(float), 256));
+  attn_bwd_prep_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>((const T*)dout, (const T*)out, lse, t, H, delta, nlse2, sidx);
   cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
   dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
-  attn_bwd_umma_kernel<T><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, scale, (T*)dqkv,
-                                                               dq_acc);
-  attn_dq_finish_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>(dq_acc, t * H, H, scale, (T*)dqkv);
+  if (gidx) {
+    cudaFuncSetAttribute(attn_bwd_umma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
+    attn_bwd_umma_kernel<T, true><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, scale, (T*)dqkv,
+                                                                        dq_acc, gidx, sidx, side);
+  } else {
+    cudaFuncSetAttribute(attn_bwd_umma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
+    attn_bwd_umma_kernel<T, false><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, scale, (T*)dqkv,
+                                                                         dq_acc, nullptr, nullptr, nullptr);
+  }
+  attn_dq_finish_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>(dq_acc, t * H, H, scale, (T*)dqkv, sidx);
   count_launches(3);
+  if (gidx && n_dup > 0) {
+    attn_dup_add_kernel<T><<<(unsigned)ceil_div(n_dup * 2 * H, 256), 256, 0, stream>>>(side, dup_point, n_dup, H, (T*)dqkv);
+    count_launches(1);
+  }
   B2PC_CHECK_LAUNCH("patch_attn_bwd(tcgen05)");
   return B2PC_OK;
 }
 
 inline int launch_attn_bwd_umma(const void* dout, const void* qkv, const void* out, const float* lse, int dtype, const int32_t* cu,
                                 int n_seq, int max_seqlen, int64_t t, int H, int D, float scale, void* dqkv, void* ws,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, const int32_t* gidx = nullptr, const int32_t* sidx = nullptr,
+                                const int32_t* dup_point = nullptr, int64_t n_dup = 0) {
   (void)D;
   if (n_seq == 0 || t == 0) return B2PC_OK;
   if (dtype == B2PC_F16)
-    return launch_attn_bwd_umma_t<__half>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, scale, dqkv, ws, stream);
-  return launch_attn_bwd_umma_t<__nv_bfloat16>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, scale, dqkv, ws, stream);
+    return launch_attn_bwd_umma_t<__half>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, scale, dqkv, ws, stream, gidx, sidx, dup_point, n_dup);
+  return launch_attn_bwd_umma_t<__nv_bfloat16>(dout, qkv, out, lse, cu, n_seq, max_seqlen, t, H, scale, dqkv, ws, stream, gidx, sidx, dup_point,
+                                               n_dup);
 }
 
 }  // namespace b2pc

@@ -260,6 +260,47 @@ int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* wo
   return launch_colsum(x, dtype, n, c, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// ---- serialized attention (gather-fused patch attention) -----------------------------------------------------------------
+int b2pc_serialized_attn_fwd(const void* qkv_points, int dtype, const int32_t* gidx, const int32_t* sidx, const int32_t* cu_seqlens,
+                             int n_seq, int max_seqlen, int64_t t_pad, int heads, int head_dim, float scale, void* out_points,
+                             float* lse, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(qkv_points && gidx && sidx && cu_seqlens && out_points && lse, "serialized_attn_fwd: null pointer");
+  B2PC_CHECK_ARG(n_seq >= 0 && max_seqlen >= 0 && t_pad >= 0 && heads > 0 && head_dim > 0, "serialized_attn_fwd: bad sizes");
+#ifndef B2PC_NO_UMMA
+  if (attn_umma_supported(dtype, head_dim))
+    return launch_attn_fwd_umma(qkv_points, dtype, cu_seqlens, n_seq, max_seqlen, t_pad, heads, head_dim, scale, out_points, lse,
+                                (cudaStream_t)stream, gidx, sidx);
+#endif
+  set_error("serialized_attn_fwd: needs the tcgen05 kernel (fp16/bf16, head_dim 16); got dtype %d head_dim %d", dtype, head_dim);
+  return B2PC_ERR_UNSUPPORTED;
+}
+
+size_t b2pc_serialized_attn_bwd_workspace_bytes(int64_t t_pad, int heads, int head_dim, int64_t n_dup) {
+#ifndef B2PC_NO_UMMA
+  return attn_bwd_umma_workspace_bytes(t_pad, heads, head_dim, n_dup);
+#else
+  return 0;
+#endif
+}
+
+int b2pc_serialized_attn_bwd(const void* dout_points, const void* qkv_points, const void* out_points, const float* lse, int dtype,
+                             const int32_t* gidx, const int32_t* sidx, const int32_t* dup_point, int64_t n_dup,
+                             const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t_pad, int heads, int head_dim, float scale,
+                             void* dqkv_points, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(dout_points && qkv_points && out_points && lse && gidx && sidx && cu_seqlens && dqkv_points && workspace,
+                 "serialized_attn_bwd: null pointer");
+  B2PC_CHECK_ARG(n_dup == 0 || dup_point, "serialized_attn_bwd: dup_point missing");
+#ifndef B2PC_NO_UMMA
+  if (attn_umma_supported(dtype, head_dim)) {
+    if (workspace_bytes < attn_bwd_umma_workspace_bytes(t_pad, heads, head_dim, n_dup)) { set_error("serialized_attn_bwd: workspace too small"); return B2PC_ERR_WORKSPACE; }
+    return launch_attn_bwd_umma(dout_points, qkv_points, out_points, lse, dtype, cu_seqlens, n_seq, max_seqlen, t_pad, heads, head_dim, scale,
+                                dqkv_points, workspace, (cudaStream_t)stream, gidx, sidx, dup_point, n_dup);
+  }
+#endif
+  set_error("serialized_attn_bwd: needs the tcgen05 kernel (fp16/bf16, head_dim 16); got dtype %d head_dim %d", dtype, head_dim);
+  return B2PC_ERR_UNSUPPORTED;
+}
+
 // ---- fused residual glue ------------------------------------------------------------------------------------------------
 int b2pc_fused_residual_fwd(const float* shortcut, const void* x, int dtype, const float* u, float keep, const float* gamma_a,
                             const float* beta_a, float eps_a, const float* gamma_b, const float* beta_b, float eps_b, int64_t n, int c,

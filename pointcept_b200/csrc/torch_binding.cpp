@@ -157,6 +157,46 @@ struct PatchAttentionFn : public torch::autograd::Function<PatchAttentionFn> {
   }
 };
 
+// ---- serialized attention: [order] gather -> patch attention -> [inverse] gather as ONE operator (point rows in, point rows out) ----------
+struct SerializedAttentionFn : public torch::autograd::Function<SerializedAttentionFn> {
+  static Tensor forward(AutogradContext* ctx, Tensor qkv, Tensor gidx, Tensor sidx, Tensor dup_point, Tensor cu, int64_t max_seqlen,
+                        int64_t heads, double scale) {
+    B2PC_GUARD(qkv);
+    TORCH_CHECK(qkv.scalar_type() == at::kHalf || qkv.scalar_type() == at::kBFloat16, "serialized attention takes fp16 or bf16 qkv");
+    qkv = qkv.contiguous();
+    const int64_t n = qkv.size(0), c3 = qkv.size(1), H = heads, D = c3 / (3 * H), t_pad = gidx.size(0);
+    TORCH_CHECK(c3 == 3 * H * D && gidx.scalar_type() == at::kInt && sidx.scalar_type() == at::kInt && cu.scalar_type() == at::kInt,
+                "serialized attention: qkv [N, 3*H*D], int32 index tables");
+    Tensor out = at::empty({n, H * D}, qkv.options());
+    Tensor lse = at::empty({H, t_pad}, qkv.options().dtype(at::kFloat));
+    check(b2pc_serialized_attn_fwd(qkv.data_ptr(), dt(qkv), gidx.data_ptr<int32_t>(), sidx.data_ptr<int32_t>(), cu.data_ptr<int32_t>(),
+                                   (int)cu.numel() - 1, (int)max_seqlen, t_pad, (int)H, (int)D, (float)scale, out.data_ptr(),
+                                   lse.data_ptr<float>(), cur_stream()),
+          "serialized_attn_fwd");
+    ctx->save_for_backward({qkv, out, lse, gidx, sidx, dup_point, cu});
+    ctx->saved_data["max_seqlen"] = max_seqlen;
+    ctx->saved_data["heads"] = heads;
+    ctx->saved_data["scale"] = scale;
+    return out;
+  }
+  static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    auto s = ctx->get_saved_variables();
+    Tensor qkv = s[0], out = s[1], lse = s[2], gidx = s[3], sidx = s[4], dup_point = s[5], cu = s[6];
+    B2PC_GUARD(qkv);
+    Tensor dout = grads[0].contiguous();
+    if (dout.scalar_type() != qkv.scalar_type()) dout = dout.to(qkv.scalar_type());
+    const int64_t H = ctx->saved_data["heads"].toInt(), D = qkv.size(1) / (3 * H), t_pad = gidx.size(0), n_dup = dup_point.numel();
+    Tensor dqkv = at::empty_like(qkv);
+    Tensor ws = workspace(b2pc_serialized_attn_bwd_workspace_bytes(t_pad, (int)H, (int)D, n_dup), qkv);
+    check(b2pc_serialized_attn_bwd(dout.data_ptr(), qkv.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), dt(qkv), gidx.data_ptr<int32_t>(),
+                                   sidx.data_ptr<int32_t>(), n_dup ? dup_point.data_ptr<int32_t>() : nullptr, n_dup, cu.data_ptr<int32_t>(),
+                                   (int)cu.numel() - 1, (int)ctx->saved_data["max_seqlen"].toInt(), t_pad, (int)H, (int)D,
+                                   (float)ctx->saved_data["scale"].toDouble(), dqkv.data_ptr(), ws.data_ptr(), (size_t)ws.numel(), cur_stream()),
+          "serialized_attn_bwd");
+    return {dqkv, Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+  }
+};
+
 // ---- sparse convolution -----------------------------------------------------------------------------------------------------------
 Tensor gather_gemm(const Tensor& feat, const Tensor& w, const Tensor& bias, const Tensor& pair, int64_t n_out, int c_in, int c_out,
                    int kv, bool transpose_w, bool flip, int impl) {
@@ -491,6 +531,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return FusedResidualFn::apply(shortcut, x, u, keep, ga, ba, eps_a, gb, bb, eps_b, emit_half);
   });
   m.def("gelu", [](Tensor x) { return GeluFn::apply(x); });
+  m.def("serialized_attention", [](Tensor qkv, Tensor gidx, Tensor sidx, Tensor dup_point, Tensor cu, int64_t max_seqlen, int64_t heads,
+                                   double scale) { return SerializedAttentionFn::apply(qkv, gidx, sidx, dup_point, cu, max_seqlen, heads, scale); });
   m.def("make_cast_plan", &make_cast_plan);
   m.def("run_cast_plan", &run_cast_plan);
   m.def("drop_path_add", [](Tensor s, Tensor x, double keep) { return DropPathAddFn::apply(s, x, keep); });

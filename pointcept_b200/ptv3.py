@@ -172,9 +172,33 @@ class SerializedAttention(PointModule):
             point[key] = (order_pad, primary_pos, dup_slots, order_pad[dup_slots])
         return point[key]
 
+    fused = True   # class switch: gather-fused serialized attention (one operator) when the compiled binding + tcgen05 path apply
+
+    @torch.no_grad()
+    def _fused_tables(self, point):
+        """int32 tables of the gather-fused operator: gidx[t] = point row read by padded slot t; sidx[t] = point row written by
+        slot t (its primary slot) or -(r+1) for the r-th borrowed filler slot; dup_point[r] = the point behind filler r."""
+        key = f"_attn_fused_{self.order_index}"
+        if key not in point:
+            order_pad, _, dup_slots, dup_points = self._gather_indices(point)
+            gidx = order_pad.int()
+            sidx = gidx.clone()
+            if dup_slots.numel() > 0:
+                sidx[dup_slots] = -(torch.arange(dup_slots.numel(), device=gidx.device, dtype=torch.int32) + 1)
+            point[key] = (gidx, sidx, dup_points.int())
+        return point[key]
+
     def forward(self, point):
         H, K, C = self.num_heads, self.patch_size, self.channels
         _, _, cu_seqlens = self.get_padding_and_inverse(point)
+        B = ops.binding()
+        if B is not None and SerializedAttention.fused and C // H == 16 and ops.get_impl() != 1 and point.feat.is_cuda:
+            gidx, sidx, dup_point = self._fused_tables(point)
+            qkv = self.qkv(point.feat)
+            # bf16 at the operator boundary whatever the autocast dtype, exactly as the reference (ptv3m1:209)
+            feat = B.serialized_attention(qkv.to(torch.bfloat16), gidx, sidx, dup_point, cu_seqlens, K, H, float(self.scale)).to(qkv.dtype)
+            point.feat = self.proj_drop(self.proj(feat))
+            return point
         order_pad, primary_pos, dup_slots, dup_points = self._gather_indices(point)
         qkv = serialized_gather(self.qkv(point.feat), order_pad, primary_pos, None, K, dup=(dup_slots, dup_points))
         # bf16 at the operator boundary whatever the autocast dtype, exactly as the reference (ptv3m1:209)

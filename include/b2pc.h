@@ -233,6 +233,21 @@ int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks
 int b2pc_gelu_fwd(const void* x, int dtype, int64_t n_elems, void* y, b2pc_stream_t stream);
 int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, void* dx, b2pc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Built-in per-entry-point timing (bench.py's roofline leg; binding independent because it lives below the C ABI).
+ * While enabled, every hot entry point brackets its kernels with a CUDA-event pair on the caller's stream and records the
+ * ALGORITHMIC work of the call (compulsory bytes, and flops where the host knows them).
+ * b2pc_profile_collect synchronises the recorded events and aggregates per entry point.
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  B2PC_P_ATTN_FWD = 0, B2PC_P_ATTN_BWD = 1, B2PC_P_CONV = 2, B2PC_P_WGRAD = 3, B2PC_P_ENCODE = 4, B2PC_P_SORT = 5,
+  B2PC_P_RULEBOOK_SUBM = 6, B2PC_P_RULEBOOK_STRIDED = 7, B2PC_P_PADDING = 8, B2PC_P_FUSED_RESIDUAL = 9, B2PC_P_LAYER_NORM = 10,
+  B2PC_P_SEGMENT_MAX = 11, B2PC_P_COLSUM = 12, B2PC_P_OTHER = 13, B2PC_P_COUNT = 14
+};
+typedef struct { int id; long long calls; double ms; double flops; double bytes; } b2pc_profile_entry;
+void b2pc_profile_enable(int on);                           /* on != 0: clear the records and start; 0: stop */
+int b2pc_profile_collect(b2pc_profile_entry* out, int max_entries);   /* returns the number of entries written (<= B2PC_P_COUNT) */
+
 #ifdef __cplusplus
 }
 #endif

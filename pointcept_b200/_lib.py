@@ -16,6 +16,22 @@ BINDING_PATH = os.path.join(BINDING_DIR, "_b2pc_torch.so")
 _lib = None
 
 c_i32p = ctypes.c_void_p
+
+
+class ProfileEntry(ctypes.Structure):
+    _fields_ = [("id", ctypes.c_int), ("calls", ctypes.c_longlong), ("ms", ctypes.c_double), ("flops", ctypes.c_double),
+                ("bytes", ctypes.c_double)]
+
+
+PROFILE_NAMES = ["attn_fwd", "attn_bwd", "conv_gather_gemm", "conv_bwd_weight", "serialize_encode", "serialize_sort", "rulebook_subm",
+                 "rulebook_strided", "patch_padding", "fused_residual", "layer_norm", "segment_max", "colsum", "other"]
+
+
+def profile_collect():
+    """-> {entry point name: dict(calls, ms, flops, bytes)} for the calls made since b2pc_profile_enable(1)"""
+    buf = (ProfileEntry * 32)()
+    n = lib().b2pc_profile_collect(buf, 32)
+    return {PROFILE_NAMES[buf[i].id]: dict(calls=int(buf[i].calls), ms=buf[i].ms, flops=buf[i].flops, bytes=buf[i].bytes) for i in range(n)}
 _SIGS = {
     "b2pc_version": (ctypes.c_int, []),
     "b2pc_last_error": (ctypes.c_char_p, []),
@@ -70,6 +86,8 @@ _SIGS = {
     "b2pc_colsum_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
     "b2pc_colsum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_size_t, ctypes.c_void_p]),
+    "b2pc_profile_enable": (None, [ctypes.c_int]),
+    "b2pc_profile_collect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "b2pc_serialized_attn_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p]),

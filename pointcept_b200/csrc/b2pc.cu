@@ -17,6 +17,8 @@
 #endif
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace b2pc {
 static std::atomic<long long> g_launches{0};
@@ -32,6 +34,29 @@ void set_error(const char* fmt, ...) {
 
 using namespace b2pc;
 
+// ---- built-in timing of the entry points (b2pc_profile_*) ------------------------------------------------------------------
+namespace {
+struct ProfRec { int id; cudaEvent_t e0, e1; double flops, bytes; };
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t s; int id; double flops, bytes; cudaEvent_t e0{nullptr};
+  ProfScope(b2pc_stream_t stream, int id_, double fl, double by) : s((cudaStream_t)stream), id(id_), flops(fl), bytes(by) {
+    if (g_prof_on.load(std::memory_order_relaxed)) { cudaEventCreate(&e0); cudaEventRecord(e0, s); }
+  }
+  ~ProfScope() {
+    if (!e0) return;
+    cudaEvent_t e1;
+    cudaEventCreate(&e1);
+    cudaEventRecord(e1, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(ProfRec{id, e0, e1, flops, bytes});
+  }
+};
+}  // namespace
+#define B2PC_PROF(stream, id, flops, bytes) ProfScope prof_scope__((stream), (id), (double)(flops), (double)(bytes))
+
 // B2PC_CONV_V1=1 selects the first-generation (round 1) tcgen05 sparse-conv kernels for A/B runs
 static bool conv_v1() {
   static const bool v = [] { const char* e = getenv("B2PC_CONV_V1"); return e && atoi(e) != 0; }();
@@ -46,6 +71,7 @@ long long b2pc_launch_count(void) { return g_launches.load(std::memory_order_rel
 
 int b2pc_serialize_encode(const int32_t* grid_coord, const int64_t* batch, int64_t n, int depth, const int* orders_host,
                           int n_orders, int64_t* code, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_ENCODE, 0, (double)n * (20.0 + 8.0 * n_orders));
   B2PC_CHECK_ARG(grid_coord && code && orders_host, "serialize_encode: null pointer");
   return launch_encode(grid_coord, batch, n, depth, orders_host, n_orders, code, (cudaStream_t)stream);
 }
@@ -54,12 +80,14 @@ size_t b2pc_serialize_sort_workspace_bytes(int64_t n, int n_orders) { return sor
 
 int b2pc_serialize_sort(const int64_t* code, int64_t n, int n_orders, int key_bits, int64_t* order, int64_t* inverse,
                         void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_SORT, 0, (double)n * n_orders * ((key_bits + 7) / 8) * 24.0);
   B2PC_CHECK_ARG(code && order && inverse && workspace, "serialize_sort: null pointer");
   return launch_sort(code, n, n_orders, key_bits, order, inverse, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int b2pc_patch_padding(const int64_t* offset, int batch_size, int patch_size, int64_t n, int64_t t_pad, int n_seq,
                        int64_t* pad, int64_t* unpad, int32_t* cu_seqlens, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_PADDING, 0, 8.0 * t_pad + 8.0 * n);
   B2PC_CHECK_ARG(offset && pad && unpad && cu_seqlens, "patch_padding: null pointer");
   return launch_padding(offset, batch_size, patch_size, n, t_pad, n_seq, pad, unpad, cu_seqlens, (cudaStream_t)stream);
 }
@@ -67,6 +95,7 @@ int b2pc_patch_padding(const int64_t* offset, int batch_size, int patch_size, in
 // ---- attention ------------------------------------------------------------------------------------
 int b2pc_patch_attn_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t,
                         int heads, int head_dim, float scale, void* out, float* lse, int impl, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_ATTN_FWD, 4.0 * t * max_seqlen * heads * head_dim, 16.0 * t * heads * head_dim);
   B2PC_CHECK_ARG(qkv && cu_seqlens && out && lse, "patch_attn_fwd: null pointer");
   B2PC_CHECK_ARG(dtype == B2PC_F16 || dtype == B2PC_BF16, "patch_attn_fwd: dtype must be fp16 or bf16 (got %d)", dtype);
   B2PC_CHECK_ARG(n_seq >= 0 && max_seqlen >= 0 && t >= 0 && heads > 0 && head_dim > 0, "patch_attn_fwd: bad sizes");
@@ -95,6 +124,7 @@ size_t b2pc_patch_attn_bwd_workspace_bytes(int64_t t, int heads, int head_dim) {
 int b2pc_patch_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse, int dtype,
                         const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t, int heads, int head_dim,
                         float scale, void* dqkv, void* workspace, size_t workspace_bytes, int impl, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_ATTN_BWD, 10.0 * t * max_seqlen * heads * head_dim, 32.0 * t * heads * head_dim);
   B2PC_CHECK_ARG(dout && qkv && out && lse && cu_seqlens && dqkv && workspace, "patch_attn_bwd: null pointer");
   B2PC_CHECK_ARG(dtype == B2PC_F16 || dtype == B2PC_BF16, "patch_attn_bwd: dtype must be fp16 or bf16 (got %d)", dtype);
   if (workspace_bytes < b2pc_patch_attn_bwd_workspace_bytes(t, heads, head_dim)) { set_error("patch_attn_bwd: workspace too small"); return B2PC_ERR_WORKSPACE; }
@@ -116,6 +146,7 @@ size_t b2pc_rulebook_workspace_bytes(int64_t n, int kv) { return rulebook_worksp
 
 int b2pc_rulebook_subm(const int32_t* indices, int64_t n, const int* spatial_shape_host, const int* ksize_host,
                        const int* dilation_host, int32_t* pair, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_RULEBOOK_SUBM, 0, (double)n * (16.0 + 4.0 * ksize_host[0] * ksize_host[1] * ksize_host[2]));
   B2PC_CHECK_ARG(indices && spatial_shape_host && ksize_host && pair && workspace, "rulebook_subm: null pointer");
   return launch_rulebook_subm(indices, n, spatial_shape_host, ksize_host, dilation_host, pair, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -123,6 +154,7 @@ int b2pc_rulebook_subm(const int32_t* indices, int64_t n, const int* spatial_sha
 int b2pc_rulebook_strided_begin(const int32_t* indices, int64_t n, const int* spatial_shape_host, const int* ksize_host,
                                 const int* stride_host, const int* padding_host, const int* dilation_host, int64_t* num_out,
                                 void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_RULEBOOK_STRIDED, 0, 16.0 * n);
   B2PC_CHECK_ARG(indices && spatial_shape_host && ksize_host && num_out && workspace, "rulebook_strided_begin: null pointer");
   return launch_rulebook_strided_begin(indices, n, spatial_shape_host, ksize_host, stride_host, padding_host, dilation_host, num_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -131,6 +163,7 @@ int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* s
                                  const int* stride_host, const int* padding_host, const int* dilation_host, int64_t num_out_host,
                                  int32_t* out_indices, int32_t* pair_fwd, int32_t* pair_bwd, void* workspace, size_t workspace_bytes,
                                  b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_RULEBOOK_STRIDED, 0, (double)(n + num_out_host) * (16.0 + 4.0 * ksize_host[0] * ksize_host[1] * ksize_host[2]));
   B2PC_CHECK_ARG(indices && spatial_shape_host && ksize_host && out_indices && pair_fwd && pair_bwd && workspace, "rulebook_strided_finish: null pointer");
   return launch_rulebook_strided_finish(indices, n, spatial_shape_host, ksize_host, stride_host, padding_host, dilation_host, num_out_host, out_indices, pair_fwd, pair_bwd, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -148,6 +181,8 @@ size_t b2pc_spconv_gather_gemm_workspace_bytes(int64_t n_out, int c_in, int c_ou
 int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bias, const int32_t* pair, int64_t pair_stride,
                             int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, int dtype,
                             void* out, void* workspace, size_t workspace_bytes, int impl, b2pc_stream_t stream) {
+  const double es__ = dtype == B2PC_F32 ? 4.0 : 2.0;
+  B2PC_PROF(stream, B2PC_P_CONV, 0, es__ * ((double)n_in * c_in + (double)n_out * c_out + (double)kv * c_in * c_out) + 4.0 * kv * n_out);
   B2PC_CHECK_ARG(feat && weight && pair && out, "spconv_gather_gemm: null pointer");
   B2PC_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && kv > 0 && pair_stride >= n_out, "spconv_gather_gemm: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
@@ -188,6 +223,8 @@ size_t b2pc_spconv_bwd_weight_workspace_bytes(int64_t n_out, int c_in, int c_out
 int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t* pair, int64_t pair_stride, int64_t n_in,
                            int64_t n_out, int c_in, int c_out, int kv, int dtype, float* dweight, void* workspace,
                            size_t workspace_bytes, int impl, b2pc_stream_t stream) {
+  const double es__ = dtype == B2PC_F32 ? 4.0 : 2.0;
+  B2PC_PROF(stream, B2PC_P_WGRAD, 0, es__ * ((double)n_in * c_in + (double)n_out * c_out) + 4.0 * kv * n_out + 4.0 * kv * c_in * c_out);
   B2PC_CHECK_ARG(feat_in && dout && pair && dweight && workspace, "spconv_bwd_weight: null pointer");
   B2PC_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && kv > 0 && pair_stride >= n_out, "spconv_bwd_weight: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
@@ -214,12 +251,14 @@ int b2pc_spconv_bwd_weight(const void* feat_in, const void* dout, const int32_t*
 // ---- serialized pooling (segment max over runs of the sorted order) --------------------------------------------------------
 int b2pc_segment_max_fwd(const void* x, int dtype, const int64_t* order, const int64_t* seg_start, const int64_t* seg_len, int64_t m,
                          int c, void* out, int32_t* arg, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_SEGMENT_MAX, 0, 0);
   B2PC_CHECK_ARG(x && order && seg_start && seg_len && out && arg, "segment_max_fwd: null pointer");
   B2PC_CHECK_ARG(m >= 0 && c > 0, "segment_max_fwd: bad sizes");
   return launch_segment_max_fwd(x, dtype, order, seg_start, seg_len, m, c, out, arg, (cudaStream_t)stream);
 }
 
 int b2pc_segment_max_bwd(const void* dout, int dtype, const int32_t* arg, int64_t m, int c, int64_t n, void* dx, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_SEGMENT_MAX, 0, 0);
   B2PC_CHECK_ARG(dout && arg && dx, "segment_max_bwd: null pointer");
   B2PC_CHECK_ARG(m >= 0 && c > 0 && n >= 0, "segment_max_bwd: bad sizes");
   return launch_segment_max_bwd(dout, dtype, arg, m, c, n, dx, (cudaStream_t)stream);
@@ -228,6 +267,7 @@ int b2pc_segment_max_bwd(const void* dout, int dtype, const int32_t* arg, int64_
 // ---- glue: fused LayerNorm ---------------------------------------------------------------------------------------
 int b2pc_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t n, int c, float eps, void* y,
                         int y_dtype, float* mean, float* rstd, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_LAYER_NORM, 0, (double)n * c * 6.0);
   B2PC_CHECK_ARG(x && gamma && y && mean && rstd, "layer_norm_fwd: null pointer");
   return launch_layer_norm_fwd(x, x_dtype, gamma, beta, n, c, eps, y, y_dtype, mean, rstd, (cudaStream_t)stream);
 }
@@ -237,6 +277,7 @@ size_t b2pc_layer_norm_bwd_workspace_bytes(int64_t n, int c) { return layer_norm
 int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
                         const float* rstd, int64_t n, int c, void* dx, float* dgamma, float* dbeta, void* workspace,
                         size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_LAYER_NORM, 0, (double)n * c * 8.0);
   B2PC_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && workspace, "layer_norm_bwd: null pointer");
   return launch_layer_norm_bwd(dy, y_dtype, x, x_dtype, gamma, mean, rstd, n, c, dx, dgamma, dbeta, workspace, workspace_bytes,
                                (cudaStream_t)stream);
@@ -244,11 +285,13 @@ int b2pc_layer_norm_bwd(const void* dy, int y_dtype, const void* x, int x_dtype,
 
 int b2pc_rowscale_add(const void* shortcut, int s_dtype, const void* x, int x_dtype, const float* rowscale, int64_t n, int c, void* out,
                       b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
   B2PC_CHECK_ARG(shortcut && x && rowscale && out, "rowscale_add: null pointer");
   return launch_rowscale_add(shortcut, s_dtype, x, x_dtype, rowscale, n, c, out, (cudaStream_t)stream);
 }
 
 int b2pc_rowscale(const void* dy, int s_dtype, const float* rowscale, int64_t n, int c, void* dx, int x_dtype, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
   B2PC_CHECK_ARG(dy && rowscale && dx, "rowscale: null pointer");
   return launch_rowscale(dy, s_dtype, rowscale, n, c, dx, x_dtype, (cudaStream_t)stream);
 }
@@ -256,6 +299,7 @@ int b2pc_rowscale(const void* dy, int s_dtype, const float* rowscale, int64_t n,
 size_t b2pc_colsum_workspace_bytes(int64_t n, int c) { return colsum_workspace_bytes(n, c); }
 
 int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_COLSUM, 0, (double)n * c * (dtype == B2PC_F32 ? 4.0 : 2.0));
   B2PC_CHECK_ARG(x && out && workspace, "colsum: null pointer");
   return launch_colsum(x, dtype, n, c, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -264,6 +308,7 @@ int b2pc_colsum(const void* x, int dtype, int64_t n, int c, float* out, void* wo
 int b2pc_serialized_attn_fwd(const void* qkv_points, int dtype, const int32_t* gidx, const int32_t* sidx, const int32_t* cu_seqlens,
                              int n_seq, int max_seqlen, int64_t t_pad, int heads, int head_dim, float scale, void* out_points,
                              float* lse, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_ATTN_FWD, 4.0 * t_pad * max_seqlen * heads * head_dim, 16.0 * t_pad * heads * head_dim);
   B2PC_CHECK_ARG(qkv_points && gidx && sidx && cu_seqlens && out_points && lse, "serialized_attn_fwd: null pointer");
   B2PC_CHECK_ARG(n_seq >= 0 && max_seqlen >= 0 && t_pad >= 0 && heads > 0 && head_dim > 0, "serialized_attn_fwd: bad sizes");
 #ifndef B2PC_NO_UMMA
@@ -287,6 +332,7 @@ int b2pc_serialized_attn_bwd(const void* dout_points, const void* qkv_points, co
                              const int32_t* gidx, const int32_t* sidx, const int32_t* dup_point, int64_t n_dup,
                              const int32_t* cu_seqlens, int n_seq, int max_seqlen, int64_t t_pad, int heads, int head_dim, float scale,
                              void* dqkv_points, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_ATTN_BWD, 10.0 * t_pad * max_seqlen * heads * head_dim, 32.0 * t_pad * heads * head_dim);
   B2PC_CHECK_ARG(dout_points && qkv_points && out_points && lse && gidx && sidx && cu_seqlens && dqkv_points && workspace,
                  "serialized_attn_bwd: null pointer");
   B2PC_CHECK_ARG(n_dup == 0 || dup_point, "serialized_attn_bwd: dup_point missing");
@@ -305,6 +351,7 @@ int b2pc_serialized_attn_bwd(const void* dout_points, const void* qkv_points, co
 int b2pc_fused_residual_fwd(const float* shortcut, const void* x, int dtype, const float* u, float keep, const float* gamma_a,
                             const float* beta_a, float eps_a, const float* gamma_b, const float* beta_b, float eps_b, int64_t n, int c,
                             float* r, void* r16, void* y, float* stat_a, float* stat_b, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_FUSED_RESIDUAL, 0, (double)n * c * (8.0 + (dtype == B2PC_F32 ? 4.0 : 2.0) * (1 + (r16 != nullptr) + (y != nullptr))));
   FusedResArgs a{shortcut, x, u, keep, gamma_a, beta_a, gamma_b, beta_b, eps_a, eps_b, n, c, r, r16, y, stat_a, stat_b};
   return launch_fused_residual_fwd(a, dtype, (cudaStream_t)stream);
 }
@@ -315,11 +362,13 @@ int b2pc_fused_residual_bwd(const float* dr_out, const void* dr16, const void* d
                             const float* u, float keep, const float* gamma_a, const float* gamma_b, const float* stat_a,
                             const float* stat_b, int64_t n, int c, float* d_shortcut, void* dx, float* dgamma_a, float* dbeta_a,
                             float* dgamma_b, float* dbeta_b, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_FUSED_RESIDUAL, 0, (double)n * c * (12.0 + (dtype == B2PC_F32 ? 4.0 : 2.0) * (2 + (dr16 != nullptr) + (dy != nullptr))));
   FusedResBwdArgs a{dr_out, dr16, dy, r, x, u, keep, gamma_a, gamma_b, stat_a, stat_b, n, c, d_shortcut, dx, nullptr};
   return launch_fused_residual_bwd(a, dtype, dgamma_a, dbeta_a, dgamma_b, dbeta_b, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks, int dst_dtype, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
   return launch_multi_cast(plan_device, n_items, total_blocks, dst_dtype, (cudaStream_t)stream);
 }
 
@@ -329,6 +378,7 @@ static int gelu_grid(int64_t total4) {
 }
 
 int b2pc_gelu_fwd(const void* x, int dtype, int64_t n_elems, void* y, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
   B2PC_CHECK_ARG(x && y && n_elems >= 0 && n_elems % 4 == 0, "gelu_fwd: bad arguments");
   if (n_elems == 0) return B2PC_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -345,6 +395,7 @@ int b2pc_gelu_fwd(const void* x, int dtype, int64_t n_elems, void* y, b2pc_strea
 }
 
 int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, void* dx, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
   B2PC_CHECK_ARG(dy && x && dx && n_elems >= 0 && n_elems % 4 == 0, "gelu_bwd: bad arguments");
   if (n_elems == 0) return B2PC_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -358,6 +409,34 @@ int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, voi
   count_launches(1);
   B2PC_CHECK_LAUNCH("gelu_bwd");
   return B2PC_OK;
+}
+
+void b2pc_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (on) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+  }
+  g_prof_on.store(on != 0);
+}
+
+int b2pc_profile_collect(b2pc_profile_entry* out, int max_entries) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  b2pc_profile_entry agg[B2PC_P_COUNT];
+  for (int i = 0; i < B2PC_P_COUNT; ++i) agg[i] = b2pc_profile_entry{i, 0, 0.0, 0.0, 0.0};
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.id >= 0 && r.id < B2PC_P_COUNT) {
+      agg[r.id].calls += 1; agg[r.id].ms += ms; agg[r.id].flops += r.flops; agg[r.id].bytes += r.bytes;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  int n = 0;
+  for (int i = 0; i < B2PC_P_COUNT && n < max_entries; ++i)
+    if (agg[i].calls > 0) out[n++] = agg[i];
+  return n;
 }
 
 }  // extern "C"

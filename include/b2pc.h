@@ -103,15 +103,18 @@ int b2pc_patch_attn_bwd(const void* dout, const void* qkv, const void* out, cons
  * Rulebook form: pair[KV, N_out] int32, entry = input row feeding output row j through kernel
  * offset k = (i0*K1+i1)*K2+i2, or -1.
  * ------------------------------------------------------------------------------------------- */
-size_t b2pc_rulebook_workspace_bytes(int64_t n, int kv);
+size_t b2pc_rulebook_workspace_bytes(int64_t n, int reach);   /* submanifold: reach = 1 */
+/* strided: sized for n * reach distinct outputs, reach = prod_axis ceil(k / (s / gcd(s, d))) (1 for k = 2, s = 2) */
+size_t b2pc_rulebook_strided_workspace_bytes(int64_t n, const int* ksize_host, const int* stride_host, const int* dilation_host);
 /* Submanifold: output set == input set (same rows); padding is implied (K//2 * dilation). */
 int b2pc_rulebook_subm(const int32_t* indices, int64_t n, const int* spatial_shape_host,
                        const int* ksize_host, const int* dilation_host, int32_t* pair,
                        void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
 /* Strided (SparseConv3d): out coordinate o is active iff some input i and offset k satisfy
  * i = o*stride - padding + k*dilation.  Output rows are the distinct out coordinates in
- * ascending (b,x,y,z) order.  Two stages because M is data dependent: _begin counts the distinct
- * outputs into *num_out (device int64); the caller reads it (one host sync, as spconv does),
+ * ascending (b,x,y,z) order.  Two stages because M is data dependent: _begin writes num_out[0] = number of distinct
+ * outputs and num_out[1] = largest batch index (device int64[2]); the caller reads both (one host sync, as spconv does),
+ * passes M and batch_count = num_out[1] + 1 (bounds the sort key width; 0 = unknown) to _finish,
  * allocates out_indices [M,4], pair_fwd [KV,M], pair_bwd [KV,N] and calls _finish with the SAME
  * workspace (its contents carry over). */
 int b2pc_rulebook_strided_begin(const int32_t* indices, int64_t n, const int* spatial_shape_host,
@@ -120,7 +123,7 @@ int b2pc_rulebook_strided_begin(const int32_t* indices, int64_t n, const int* sp
                                 size_t workspace_bytes, b2pc_stream_t stream);
 int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* spatial_shape_host,
                                  const int* ksize_host, const int* stride_host, const int* padding_host,
-                                 const int* dilation_host, int64_t num_out_host, int32_t* out_indices,
+                                 const int* dilation_host, int64_t num_out_host, int batch_count_host, int32_t* out_indices,
                                  int32_t* pair_fwd, int32_t* pair_bwd, void* workspace,
                                  size_t workspace_bytes, b2pc_stream_t stream);
 

@@ -57,8 +57,9 @@ _SIGS = {
                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "b2pc_rulebook_strided_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int)] * 5 +
                                     [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "b2pc_rulebook_strided_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int)] * 3),
     "b2pc_rulebook_strided_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int)] * 5 +
-                                     [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_void_p]),
     "b2pc_spconv_gather_gemm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b2pc_spconv_gather_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

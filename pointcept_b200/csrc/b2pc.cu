@@ -142,7 +142,11 @@ int b2pc_patch_attn_bwd(const void* dout, const void* qkv, const void* out, cons
 }
 
 // ---- rulebooks --------------------------------------------------------------------------------------
-size_t b2pc_rulebook_workspace_bytes(int64_t n, int kv) { return rulebook_workspace_bytes(n, kv); }
+size_t b2pc_rulebook_workspace_bytes(int64_t n, int reach) { return rulebook_workspace_bytes(n, reach); }
+size_t b2pc_rulebook_strided_workspace_bytes(int64_t n, const int* ksize_host, const int* stride_host, const int* dilation_host) {
+  if (!ksize_host) return 0;
+  return rulebook_workspace_bytes(n, strided_reach(ksize_host, stride_host, dilation_host));
+}
 
 int b2pc_rulebook_subm(const int32_t* indices, int64_t n, const int* spatial_shape_host, const int* ksize_host,
                        const int* dilation_host, int32_t* pair, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
@@ -161,11 +165,11 @@ int b2pc_rulebook_strided_begin(const int32_t* indices, int64_t n, const int* sp
 
 int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* spatial_shape_host, const int* ksize_host,
                                  const int* stride_host, const int* padding_host, const int* dilation_host, int64_t num_out_host,
-                                 int32_t* out_indices, int32_t* pair_fwd, int32_t* pair_bwd, void* workspace, size_t workspace_bytes,
+                                 int batch_count_host, int32_t* out_indices, int32_t* pair_fwd, int32_t* pair_bwd, void* workspace, size_t workspace_bytes,
                                  b2pc_stream_t stream) {
   B2PC_PROF(stream, B2PC_P_RULEBOOK_STRIDED, 0, (double)(n + num_out_host) * (16.0 + 4.0 * ksize_host[0] * ksize_host[1] * ksize_host[2]));
   B2PC_CHECK_ARG(indices && spatial_shape_host && ksize_host && out_indices && pair_fwd && pair_bwd && workspace, "rulebook_strided_finish: null pointer");
-  return launch_rulebook_strided_finish(indices, n, spatial_shape_host, ksize_host, stride_host, padding_host, dilation_host, num_out_host, out_indices, pair_fwd, pair_bwd, workspace, workspace_bytes, (cudaStream_t)stream);
+  return launch_rulebook_strided_finish(indices, n, spatial_shape_host, ksize_host, stride_host, padding_host, dilation_host, num_out_host, batch_count_host, out_indices, pair_fwd, pair_bwd, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // ---- sparse convolution arithmetic ---------------------------------------------------------------------

@@ -103,6 +103,11 @@ __device__ __forceinline__ uint64_t strided_out_key(const int4 c, int i0, int i1
 __global__ void __launch_bounds__(256)
 strided_collect_kernel(const int4* __restrict__ indices, int64_t n, Geometry g, uint64_t* __restrict__ keys,
                        uint32_t mask, uint64_t* __restrict__ uniq, unsigned long long* __restrict__ num_out) {
+  int bmax = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bmax = max(bmax, indices[i].x);
+  bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
+  if ((threadIdx.x & 31) == 0 && bmax > 0) atomicMax(num_out + 1, (unsigned long long)bmax);   // num_out[1] = largest batch index
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int4 c = indices[i];
     for (int i0 = 0; i0 < g.k[0]; ++i0)
@@ -179,9 +184,22 @@ struct RulebookWs {
   size_t sort_bytes; int64_t slots; size_t total;
 };
 
-inline RulebookWs carve_rulebook_ws(void* ws, int64_t n, int kv) {
+// reach = how many distinct outputs one input voxel can feed: per axis the offsets i with (c + p - i*d) % s == 0, i.e.
+// ceil(k / (s / gcd(s, d))) of them (1 for the k = 2, s = 2 down-convolutions of SpUNet, 8 for k = 3, s = 2)
+inline int strided_reach(const int* k, const int* s, const int* d) {
+  int reach = 1;
+  for (int a = 0; a < 3; ++a) {
+    int sa = s ? s[a] : 1, da = d ? d[a] : 1, x = sa, y = da;
+    while (y) { const int t = x % y; x = y; y = t; }
+    const int period = sa / (x > 0 ? x : 1);
+    reach *= (k[a] + period - 1) / period;
+  }
+  return reach < 1 ? 1 : reach;
+}
+
+inline RulebookWs carve_rulebook_ws(void* ws, int64_t n, int reach) {
   RulebookWs r;
-  const int64_t cap = n * (int64_t)(kv < 1 ? 1 : kv);  // most distinct keys a strided build can see
+  const int64_t cap = n * (int64_t)(reach < 1 ? 1 : reach);  // most distinct keys a strided build can see
   r.slots = hash_slots(cap > n ? cap : n);
   char* p = (char*)ws;
   size_t off = 0;
@@ -196,7 +214,7 @@ inline RulebookWs carve_rulebook_ws(void* ws, int64_t n, int kv) {
   return r;
 }
 
-inline size_t rulebook_workspace_bytes(int64_t n, int kv) { return carve_rulebook_ws(nullptr, n, kv).total; }
+inline size_t rulebook_workspace_bytes(int64_t n, int reach) { return carve_rulebook_ws(nullptr, n, reach).total; }
 
 inline int grid_for(int64_t n) {
   int64_t b = ceil_div(n > 0 ? n : 1, 256);
@@ -241,11 +259,12 @@ inline int launch_rulebook_strided_begin(const int32_t* indices, int64_t n, cons
   Geometry g;
   int rc = check_geometry("rulebook_strided", g, shape, ksize, stride, padding, dilation);
   if (rc) return rc;
-  B2PC_CHECK_ARG(n >= 0 && n * (int64_t)g.kv < (1ll << 31), "rulebook_strided: n*kv out of range");
-  if (ws_bytes < rulebook_workspace_bytes(n, g.kv)) { set_error("rulebook_strided: workspace too small"); return B2PC_ERR_WORKSPACE; }
-  cudaMemsetAsync(num_out, 0, sizeof(int64_t), stream);
+  const int reach = strided_reach(g.k, g.s, g.d);
+  B2PC_CHECK_ARG(n >= 0 && n * (int64_t)reach < (1ll << 31), "rulebook_strided: n * reach out of range");
+  if (ws_bytes < rulebook_workspace_bytes(n, reach)) { set_error("rulebook_strided: workspace too small"); return B2PC_ERR_WORKSPACE; }
+  cudaMemsetAsync(num_out, 0, 2 * sizeof(int64_t), stream);
   if (n == 0) return B2PC_OK;
-  RulebookWs r = carve_rulebook_ws(ws, n, g.kv);
+  RulebookWs r = carve_rulebook_ws(ws, n, reach);
   hash_clear_kernel<<<grid_for(r.slots), 256, 0, stream>>>(r.keys, r.slots);
   strided_collect_kernel<<<grid_for(n), 256, 0, stream>>>((const int4*)indices, n, g, r.keys, (uint32_t)(r.slots - 1), r.uniq,
                                                           (unsigned long long*)num_out);
@@ -255,22 +274,24 @@ inline int launch_rulebook_strided_begin(const int32_t* indices, int64_t n, cons
 }
 
 inline int launch_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* shape, const int* ksize,
-                                          const int* stride, const int* padding, const int* dilation, int64_t m,
+                                          const int* stride, const int* padding, const int* dilation, int64_t m, int batch_count,
                                           int32_t* out_indices, int32_t* pair_fwd, int32_t* pair_bwd, void* ws,
                                           size_t ws_bytes, cudaStream_t stream) {
   Geometry g;
   int rc = check_geometry("rulebook_strided", g, shape, ksize, stride, padding, dilation);
   if (rc) return rc;
-  if (ws_bytes < rulebook_workspace_bytes(n, g.kv)) { set_error("rulebook_strided: workspace too small"); return B2PC_ERR_WORKSPACE; }
-  B2PC_CHECK_ARG(m >= 0 && m <= n * (int64_t)g.kv, "rulebook_strided_finish: num_out out of range");
+  const int reach = strided_reach(g.k, g.s, g.d);
+  if (ws_bytes < rulebook_workspace_bytes(n, reach)) { set_error("rulebook_strided: workspace too small"); return B2PC_ERR_WORKSPACE; }
+  B2PC_CHECK_ARG(m >= 0 && m <= n * (int64_t)reach, "rulebook_strided_finish: num_out out of range");
   if (n == 0 || m == 0) return B2PC_OK;
-  RulebookWs r = carve_rulebook_ws(ws, n, g.kv);
+  RulebookWs r = carve_rulebook_ws(ws, n, reach);
   const uint32_t mask = (uint32_t)(r.slots - 1);
   // ascending linearised (b,x,y,z): sort the distinct keys on their significant bits
-  // key < batch * prod(oshape); the batch count is not part of the geometry, allow up to 2^20 scenes
+  // key < batch_count * prod(oshape); batch_count comes back with the output count (0 = unknown: allow 2^20 scenes)
   int key_bits = 0;
   {
-    unsigned __int128 bound = ((unsigned __int128)g.oshape[0] * g.oshape[1] * g.oshape[2]) << 20;
+    const unsigned __int128 nb = batch_count > 0 ? (unsigned __int128)batch_count : ((unsigned __int128)1 << 20);
+    unsigned __int128 bound = (unsigned __int128)g.oshape[0] * g.oshape[1] * g.oshape[2] * nb;
     while (key_bits < 64 && (bound >> key_bits) != 0) ++key_bits;
   }
   rc = launch_sort((const int64_t*)r.uniq, m, 1, key_bits, r.order, r.inverse, r.sort_ws, r.sort_bytes, stream);

@@ -221,6 +221,8 @@ def rulebook_subm(indices, spatial_shape, ksize, dilation=1):
     dl, _ = _i3(dilation)
     kv = kt[0] * kt[1] * kt[2]
     pair = torch.empty((kv, n), dtype=torch.int32, device=indices.device)
+    if n == 0:
+        return pair
     L = _lib.lib()
     ws = _ws(L.b2pc_rulebook_workspace_bytes(n, 1), indices.device)
     _lib.check(L.b2pc_rulebook_subm(_p(indices), n, shp, ks, dl, _p(pair), _p(ws), ws.numel(), _stream()), "rulebook_subm")
@@ -244,15 +246,18 @@ def rulebook_strided(indices, spatial_shape, ksize, stride, padding=0, dilation=
     out_shape = [(shape_t[a] + 2 * pdt[a] - dlt[a] * (kt[a] - 1) - 1) // stt[a] + 1 for a in range(3)]
     L = _lib.lib()
     dev = indices.device
-    ws = _ws(L.b2pc_rulebook_workspace_bytes(n, kv), dev)
-    num = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n == 0:
+        z = torch.empty((kv, 0), dtype=torch.int32, device=dev)
+        return torch.empty((0, 4), dtype=torch.int32, device=dev), out_shape, z, z.clone()
+    ws = _ws(L.b2pc_rulebook_strided_workspace_bytes(n, ks, st, dl), dev)
+    num = torch.zeros(2, dtype=torch.int64, device=dev)
     _lib.check(L.b2pc_rulebook_strided_begin(_p(indices), n, shp, ks, st, pd, dl, _p(num), _p(ws), ws.numel(), _stream()),
                "rulebook_strided_begin")
-    m = int(num.item())
+    m, bmax = (int(v) for v in num.tolist())        # the one host sync: output count (+ the batch bound of the sort keys)
     out_indices = torch.empty((m, 4), dtype=torch.int32, device=dev)
     pair_fwd = torch.empty((kv, m), dtype=torch.int32, device=dev)
     pair_bwd = torch.empty((kv, n), dtype=torch.int32, device=dev)
-    _lib.check(L.b2pc_rulebook_strided_finish(_p(indices), n, shp, ks, st, pd, dl, m, _p(out_indices), _p(pair_fwd), _p(pair_bwd),
+    _lib.check(L.b2pc_rulebook_strided_finish(_p(indices), n, shp, ks, st, pd, dl, m, bmax + 1, _p(out_indices), _p(pair_fwd), _p(pair_bwd),
                                               _p(ws), ws.numel(), _stream()), "rulebook_strided_finish")
     return out_indices, out_shape, pair_fwd, pair_bwd
 

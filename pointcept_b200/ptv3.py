@@ -476,7 +476,10 @@ class PointTransformerV3(PointModule):
         super().__init__()
         # spatial_reorder (not a reference option): lay the level-0 points out in memory along the first space-filling
         # curve so that the rulebook gathers and the [order] / [inverse] gathers of the attention hit nearby cache lines.
-        # Results are permutation-equivalent; the returned feat is restored to the caller's point order.
+        # Results are permutation-equivalent; the returned ``feat`` is restored to the caller's point order.  Every OTHER
+        # per-point entry of the returned Point (coord, grid_coord, batch, serialized_*, sparse_conv_feat, pooling_inverse of
+        # level 1) stays in the spatial layout: index it through point["spatial_perm"] (spatial row -> caller row), or run with
+        # spatial_reorder=False when a head needs more than ``feat``.  A prepared Point is single use (asserted).
         self.spatial_reorder = spatial_reorder
         if pdnorm_bn or pdnorm_ln:
             raise NotImplementedError("PDNorm (multi-dataset prompt training) is outside the PT-v3m1 hot path")
@@ -560,6 +563,9 @@ class PointTransformerV3(PointModule):
 
     def forward(self, data_dict):
         point = data_dict if isinstance(data_dict, Point) and data_dict.get("_prepared", False) else self.prepare(data_dict)
+        if point.get("_consumed", False):
+            raise RuntimeError("this prepared Point already went through forward(); prepare() a fresh one (its feat was re-laid out)")
+        point["_consumed"] = True
         self._sync_half_shadows()
         if "_has_dp" not in self.__dict__:
             self.__dict__["_has_dp"] = any(isinstance(m, DropPath) and m.drop_prob > 0.0 for m in self.modules())

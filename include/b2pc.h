@@ -161,6 +161,17 @@ int b2pc_segment_max_fwd(const void* x, int dtype, const int64_t* order, const i
 int b2pc_segment_max_bwd(const void* dout, int dtype, const int32_t* arg, int64_t m, int c, int64_t n, void* dx,
                          b2pc_stream_t stream);
 
+/* Index side of SerializedPooling (point_transformer_v3m1_base.py:371-398) in four small launches and ONE deferred host read:
+ * clusters = runs of equal (code[0] >> 3*pooling_depth) in the order-0 sorted sequence.  All outputs are sized for N rows
+ * (code_out [n_orders, N] with row stride N); meta[0] = M (clusters), meta[1 + b] = clusters of scene b; the caller reads
+ * meta once and slices.  cluster [N] = row -> cluster id; head_pos / head_indices / lengths [M] describe the runs;
+ * code_out / batch_out / grid_out are the pooled level's codes (every order), batch ids and grid coordinates (>> depth). */
+size_t b2pc_pool_plan_workspace_bytes(int64_t n);
+int b2pc_pool_plan(const int64_t* code, int n_orders, int64_t n, const int64_t* order0, const int64_t* batch,
+                   const int32_t* grid_coord, int pooling_depth, int n_scene, int64_t* cluster, int64_t* head_pos,
+                   int64_t* head_indices, int64_t* lengths, int64_t* code_out, int64_t* batch_out, int32_t* grid_out,
+                   int64_t* meta, void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Glue on the path between the two operators: fused LayerNorm over point
  * features [N, C] as applied at point_transformer_v3m1_base.py:285,288,300 (nn.LayerNorm under

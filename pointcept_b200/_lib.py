@@ -87,6 +87,9 @@ _SIGS = {
     "b2pc_colsum_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
     "b2pc_colsum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_size_t, ctypes.c_void_p]),
+    "b2pc_pool_plan_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
+    "b2pc_pool_plan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_int] + [ctypes.c_void_p] * 9 + [ctypes.c_size_t, ctypes.c_void_p]),
     "b2pc_profile_enable": (None, [ctypes.c_int]),
     "b2pc_profile_collect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "b2pc_serialized_attn_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,

@@ -268,6 +268,19 @@ int b2pc_segment_max_bwd(const void* dout, int dtype, const int32_t* arg, int64_
   return launch_segment_max_bwd(dout, dtype, arg, m, c, n, dx, (cudaStream_t)stream);
 }
 
+size_t b2pc_pool_plan_workspace_bytes(int64_t n) { return pool_plan_workspace_bytes(n); }
+
+int b2pc_pool_plan(const int64_t* code, int n_orders, int64_t n, const int64_t* order0, const int64_t* batch, const int32_t* grid_coord,
+                   int pooling_depth, int n_scene, int64_t* cluster, int64_t* head_pos, int64_t* head_indices, int64_t* lengths,
+                   int64_t* code_out, int64_t* batch_out, int32_t* grid_out, int64_t* meta, void* workspace, size_t workspace_bytes,
+                   b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
+  B2PC_CHECK_ARG(code && order0 && batch && grid_coord && cluster && head_pos && head_indices && lengths && code_out && batch_out &&
+                 grid_out && meta && workspace, "pool_plan: null pointer");
+  return launch_pool_plan(code, n_orders, n, order0, batch, grid_coord, pooling_depth, n_scene, cluster, head_pos, head_indices, lengths,
+                          code_out, batch_out, grid_out, meta, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 // ---- glue: fused LayerNorm ---------------------------------------------------------------------------------------
 int b2pc_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t n, int c, float eps, void* y,
                         int y_dtype, float* mean, float* rstd, b2pc_stream_t stream) {

@@ -435,6 +435,34 @@ def segment_max(x, order, seg_start, seg_len):
     return SegmentMaxFn.apply(x, order, seg_start, seg_len)
 
 
+@torch.no_grad()
+def pool_plan(code, order0, batch, grid_coord, pooling_depth, n_scene):
+    """Index side of SerializedPooling (ptv3m1:371-398) on the device with one host read.
+    -> dict(cluster [N], head_pos / head_indices / lengths [M], code [n_orders, M], batch [M], grid_coord [M,3], counts list[int])"""
+    _need_cuda(code, order0, batch, grid_coord)
+    code = code.contiguous()
+    k, n = code.shape
+    dev = code.device
+    order0 = order0.contiguous()
+    batch = batch if (batch.dtype == torch.int64 and batch.is_contiguous()) else batch.long().contiguous()
+    gc = grid_coord if (grid_coord.dtype == torch.int32 and grid_coord.is_contiguous()) else grid_coord.int().contiguous()
+    i64 = dict(dtype=torch.int64, device=dev)
+    cluster, head_pos, head_idx, lengths = (torch.empty(n, **i64) for _ in range(4))
+    code_out = torch.empty((k, n), **i64)
+    batch_out = torch.empty(n, **i64)
+    grid_out = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    meta = torch.empty(1 + n_scene, **i64)
+    L = _lib.lib()
+    ws = _ws(L.b2pc_pool_plan_workspace_bytes(n), dev)
+    _lib.check(L.b2pc_pool_plan(_p(code), k, n, _p(order0), _p(batch), _p(gc), int(pooling_depth), int(n_scene), _p(cluster), _p(head_pos),
+                                _p(head_idx), _p(lengths), _p(code_out), _p(batch_out), _p(grid_out), _p(meta), _p(ws), ws.numel(), _stream()),
+               "pool_plan")
+    mh = meta.tolist()              # the single host sync of this pooling stage
+    m = int(mh[0])
+    return dict(cluster=cluster, head_pos=head_pos[:m], head_indices=head_idx[:m], lengths=lengths[:m], code=code_out[:, :m].contiguous(),
+                batch=batch_out[:m], grid_coord=grid_out[:m], counts=[int(v) for v in mh[1:]])
+
+
 class UnpoolAddFn(torch.autograd.Function):
     """out = parent + child[cluster]  (SerializedUnpooling, ptv3m1:479); the gradient of child is a segment sum over the
     parent's sorted order instead of a sort-based index_put."""

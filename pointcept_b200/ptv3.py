@@ -348,29 +348,36 @@ class SerializedPooling(PointModule):
         if pooling_depth > src["serialized_depth"]:
             pooling_depth = 0
         n = src["serialized_code"].shape[1]
-        code = src["serialized_code"] >> pooling_depth * 3
         order0 = src["serialized_order"][0]
-        sc = code[0][order0]
-        flag = torch.ones_like(sc, dtype=torch.bool)
-        flag[1:] = sc[1:] != sc[:-1]
-        cid_sorted = torch.cumsum(flag, 0) - 1
-        cluster = torch.empty_like(cid_sorted)
-        cluster[order0] = cid_sorted
-        head_pos = torch.nonzero(flag).squeeze(1)                 # host sync: number of clusters
-        head_indices = order0[head_pos]
-        lengths = torch.diff(head_pos, append=head_pos.new_full((1,), n))
-        code = code[:, head_indices]
         n_scene = len(src["offset"])
         depth = src["serialized_depth"] - pooling_depth
         key_bits = 3 * depth + max(n_scene - 1, 1).bit_length()
+        if order0.is_cuda and n > 0:
+            # device plan: 4 small launches + ONE host read (cluster count and per-scene counts together)
+            pp = ops.pool_plan(src["serialized_code"], order0, src["batch"], src["grid_coord"], pooling_depth, n_scene)
+            cluster, head_pos, head_indices, lengths = pp["cluster"], pp["head_pos"], pp["head_indices"], pp["lengths"]
+            code, batch, grid, counts_host = pp["code"], pp["batch"], pp["grid_coord"], pp["counts"]
+        else:
+            code = src["serialized_code"] >> pooling_depth * 3
+            sc = code[0][order0]
+            flag = torch.ones_like(sc, dtype=torch.bool)
+            flag[1:] = sc[1:] != sc[:-1]
+            cid_sorted = torch.cumsum(flag, 0) - 1
+            cluster = torch.empty_like(cid_sorted)
+            cluster[order0] = cid_sorted
+            head_pos = torch.nonzero(flag).squeeze(1)                 # host sync: number of clusters
+            head_indices = order0[head_pos]
+            lengths = torch.diff(head_pos, append=head_pos.new_full((1,), n))
+            code = code[:, head_indices]
+            batch = src["batch"][head_indices]
+            grid = src["grid_coord"][head_indices] >> pooling_depth
+            counts_host = torch.bincount(batch, minlength=n_scene).tolist()
         order, inverse = ops.serialize_sort(code, key_bits)
         if self.shuffle_orders:
             perm = torch.randperm(code.shape[0]).tolist()
             code = torch.stack([code[i] for i in perm])
             order = torch.stack([order[i] for i in perm])
             inverse = torch.stack([inverse[i] for i in perm])
-        batch = src["batch"][head_indices]
-        counts_host = torch.bincount(batch, minlength=n_scene).tolist()
         off, acc = [], 0
         for c in counts_host:
             acc += c
@@ -378,7 +385,7 @@ class SerializedPooling(PointModule):
         out = dict(order0=order0, lengths=lengths, head_pos=head_pos, head_indices=head_indices, cluster=cluster,
                    pooling_depth=pooling_depth,
                    serialized_code=code, serialized_order=order, serialized_inverse=inverse, serialized_depth=depth, batch=batch,
-                   grid_coord=src["grid_coord"][head_indices] >> pooling_depth, offset_host=off,
+                   grid_coord=grid, offset_host=off,
                    offset=torch.tensor(off, device=batch.device, dtype=src["offset"].dtype))
         if "grid_max_host" in src:
             out["grid_max_host"] = [g >> pooling_depth for g in src["grid_max_host"]]

@@ -220,3 +220,42 @@ def test_serialized_attention_operator_matches_gather_attention_scatter(K, H):
     o3.backward(dout.float())
     assert rel_l2(out1.detach().float(), o3.detach().bfloat16().float()) < 3e-3
     assert rel_l2(x1.grad.float(), x3.grad.bfloat16().float()) < 6e-3
+
+
+def test_pool_plan_kernels_match_the_torch_composition_bit_exact():
+    """SerializedPooling's index side (ptv3m1:371-398): the device plan (4 launches, one host read) against the op-by-op torch
+    plan (unique / cumsum / nonzero / gathers) on the same serialized level: every table bit exact."""
+    import numpy as np
+    from pointcept_b200 import synth
+    from pointcept_b200.ptv3 import SerializedPooling
+    from pointcept_b200.structure import Point
+    b = synth.make_batch(3, seed=11, target_voxels=20_000)
+    p = Point(grid_coord=torch.from_numpy(b["grid_coord"]).to(DEV), offset=torch.from_numpy(b["offset"]).to(DEV),
+              feat=torch.from_numpy(b["feat"]).to(DEV))
+    p.serialization(order=["z", "z-trans", "hilbert", "hilbert-trans"])
+    pool = SerializedPooling(32, 64, stride=2, shuffle_orders=False).to(DEV)
+    src = p
+    for level in range(3):
+        dev_plan = pool.plan(src)
+        cpu_src = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in src.items() if k != "feat"}
+        # the torch composition runs when the tables are not on CUDA; ops.serialize_sort needs CUDA, so re-sort on the device
+        code = cpu_src["serialized_code"] >> 3
+        sc = code[0][cpu_src["serialized_order"][0]]
+        flag = torch.ones_like(sc, dtype=torch.bool)
+        flag[1:] = sc[1:] != sc[:-1]
+        head_pos = torch.nonzero(flag).squeeze(1)
+        head_idx = cpu_src["serialized_order"][0][head_pos]
+        cid = torch.cumsum(flag, 0) - 1
+        cluster = torch.empty_like(cid)
+        cluster[cpu_src["serialized_order"][0]] = cid
+        n = sc.numel()
+        assert torch.equal(dev_plan["head_pos"].cpu(), head_pos) and torch.equal(dev_plan["head_indices"].cpu(), head_idx)
+        assert torch.equal(dev_plan["cluster"].cpu(), cluster)
+        assert torch.equal(dev_plan["lengths"].cpu(), torch.diff(head_pos, append=head_pos.new_full((1,), n)))
+        assert torch.equal(dev_plan["serialized_code"].cpu(), code[:, head_idx])
+        assert torch.equal(dev_plan["batch"].cpu(), cpu_src["batch"][head_idx])
+        assert torch.equal(dev_plan["grid_coord"].cpu().long(), cpu_src["grid_coord"][head_idx].long() >> 1)
+        assert dev_plan["offset_host"] == torch.cumsum(torch.bincount(cpu_src["batch"][head_idx], minlength=3), 0).tolist()
+        want_order = torch.sort(code[:, head_idx], dim=1, stable=True).indices
+        assert torch.equal(dev_plan["serialized_order"].cpu(), want_order)
+        src = dev_plan

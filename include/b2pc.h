@@ -225,7 +225,8 @@ int b2pc_serialized_attn_bwd(const void* dout_points, const void* qkv_points, co
  * x / r16 / y are `dtype` (fp32, fp16 or bf16), shortcut / r / statistics / affine parameters fp32.
  * stat_a / stat_b: [2, n] (mean, rstd) saved for the backward.  C in {32, 64, 128, 256, 512}.
  * Backward: exact adjoint.  dr_out / dr16 / dy are the gradients of the three outputs (any may be NULL);
- * d_shortcut [n,c] fp32 and dx [n,c] dtype are written; the LayerNorm parameter gradients are reduced deterministically.
+ * d_shortcut [n,c] fp32 and dx [n,c] dtype are written; the LayerNorm parameter gradients are reduced deterministically;
+ * dx_colsum [c] (optional) receives the column sums of dx = the bias gradient of the Linear that produced x.
  * ------------------------------------------------------------------------------------------- */
 int b2pc_fused_residual_fwd(const float* shortcut, const void* x, int dtype, const float* u, float keep,
                             const float* gamma_a, const float* beta_a, float eps_a, const float* gamma_b,
@@ -235,8 +236,8 @@ size_t b2pc_fused_residual_bwd_workspace_bytes(int64_t n, int c);
 int b2pc_fused_residual_bwd(const float* dr_out, const void* dr16, const void* dy, int dtype, const float* r,
                             const void* x, const float* u, float keep, const float* gamma_a, const float* gamma_b,
                             const float* stat_a, const float* stat_b, int64_t n, int c, float* d_shortcut, void* dx,
-                            float* dgamma_a, float* dbeta_a, float* dgamma_b, float* dbeta_b, void* workspace,
-                            size_t workspace_bytes, b2pc_stream_t stream);
+                            float* dgamma_a, float* dbeta_a, float* dgamma_b, float* dbeta_b, float* dx_colsum,
+                            void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
 
 /* One launch refreshes the half-precision shadows of a list of fp32 parameter tensors (what autocast does with one cast
  * kernel per weight per step, torch/amp).  plan: DEVICE array of n_items records {const float* src; void* dst;

@@ -378,10 +378,11 @@ size_t b2pc_fused_residual_bwd_workspace_bytes(int64_t n, int c) { return fused_
 int b2pc_fused_residual_bwd(const float* dr_out, const void* dr16, const void* dy, int dtype, const float* r, const void* x,
                             const float* u, float keep, const float* gamma_a, const float* gamma_b, const float* stat_a,
                             const float* stat_b, int64_t n, int c, float* d_shortcut, void* dx, float* dgamma_a, float* dbeta_a,
-                            float* dgamma_b, float* dbeta_b, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+                            float* dgamma_b, float* dbeta_b, float* dx_colsum, void* workspace, size_t workspace_bytes,
+                            b2pc_stream_t stream) {
   B2PC_PROF(stream, B2PC_P_FUSED_RESIDUAL, 0, (double)n * c * (12.0 + (dtype == B2PC_F32 ? 4.0 : 2.0) * (2 + (dr16 != nullptr) + (dy != nullptr))));
-  FusedResBwdArgs a{dr_out, dr16, dy, r, x, u, keep, gamma_a, gamma_b, stat_a, stat_b, n, c, d_shortcut, dx, nullptr};
-  return launch_fused_residual_bwd(a, dtype, dgamma_a, dbeta_a, dgamma_b, dbeta_b, workspace, workspace_bytes, (cudaStream_t)stream);
+  FusedResBwdArgs a{dr_out, dr16, dy, r, x, u, keep, gamma_a, gamma_b, stat_a, stat_b, n, c, d_shortcut, dx, nullptr, 0};
+  return launch_fused_residual_bwd(a, dtype, dgamma_a, dbeta_a, dgamma_b, dbeta_b, dx_colsum, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks, int dst_dtype, b2pc_stream_t stream) {

@@ -136,7 +136,8 @@ struct FusedResBwdArgs {
   int64_t n; int c;
   float* d_shortcut;        // [n, c] fp32 out
   void* dx;                 // [n, c] T out
-  float* part;              // [blocks][4][c]: dga, dba, dgb, dbb partial sums
+  float* part;              // [blocks][5][c]: dga, dba, dgb, dbb, colsum(dx) partial sums
+  int want_dx_colsum;       // also reduce the column sums of dx (= bias gradient of the Linear that produced x)
 };
 
 template <typename T, int V>
@@ -156,13 +157,13 @@ fused_residual_bwd_kernel(FusedResBwdArgs a) {
   T* dx = reinterpret_cast<T*>(a.dx);
   const bool ln_a = a.ga != nullptr, ln_b = a.gb != nullptr && a.dy != nullptr;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 ga[V], gb[V], aga[V], aba[V], agb[V], abb[V];
+  float4 ga[V], gb[V], aga[V], aba[V], agb[V], abb[V], adx[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int o = 4 * (sub + i * L);
     ga[i] = ln_a ? ld4<float>(a.ga + o) : z4;
     gb[i] = ln_b ? ld4<float>(a.gb + o) : z4;
-    aga[i] = aba[i] = agb[i] = abb[i] = z4;
+    aga[i] = aba[i] = agb[i] = abb[i] = adx[i] = z4;
   }
   const float inv_c = 1.f / c;
   const float inv_keep = a.u ? 1.f / a.keep : 1.f;
@@ -226,14 +227,19 @@ fused_residual_bwd_kernel(FusedResBwdArgs a) {
       const float m1 = s1 * inv_c, m2 = s2 * inv_c;
       if (ok) {
 #pragma unroll
-        for (int i = 0; i < V; ++i)
-          st4<T>(dx + row * c + 4 * (sub + i * L),
-                 make_float4(rs * (dh[i].x - m1 - xh[i].x * m2), rs * (dh[i].y - m1 - xh[i].y * m2),
-                             rs * (dh[i].z - m1 - xh[i].z * m2), rs * (dh[i].w - m1 - xh[i].w * m2)));
+        for (int i = 0; i < V; ++i) {
+          const float4 o4 = make_float4(rs * (dh[i].x - m1 - xh[i].x * m2), rs * (dh[i].y - m1 - xh[i].y * m2),
+                                        rs * (dh[i].z - m1 - xh[i].z * m2), rs * (dh[i].w - m1 - xh[i].w * m2));
+          st4<T>(dx + row * c + 4 * (sub + i * L), o4);
+          adx[i].x += o4.x; adx[i].y += o4.y; adx[i].z += o4.z; adx[i].w += o4.w;
+        }
       }
     } else if (ok) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) st4<T>(dx + row * c + 4 * (sub + i * L), dr[i]);
+      for (int i = 0; i < V; ++i) {
+        st4<T>(dx + row * c + 4 * (sub + i * L), dr[i]);
+        adx[i].x += dr[i].x; adx[i].y += dr[i].y; adx[i].z += dr[i].z; adx[i].w += dr[i].w;
+      }
     }
   }
   // block partials of the four parameter gradients, two at a time through shared memory, fixed summation order
@@ -241,20 +247,24 @@ fused_residual_bwd_kernel(FusedResBwdArgs a) {
   const int slot = warp * rpw + rin;
   float* r0s = red;
   float* r1s = red + slots * c;
-  for (int pass = 0; pass < 2; ++pass) {
-    if ((pass == 0 && !ln_a) || (pass == 1 && !ln_b)) continue;   // uniform across the grid
+  for (int pass = 0; pass < 3; ++pass) {
+    if ((pass == 0 && !ln_a) || (pass == 1 && !ln_b) || (pass == 2 && !a.want_dx_colsum)) continue;   // uniform across the grid
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      *reinterpret_cast<float4*>(r0s + slot * c + 4 * (sub + i * L)) = pass == 0 ? aga[i] : agb[i];
+      *reinterpret_cast<float4*>(r0s + slot * c + 4 * (sub + i * L)) = pass == 0 ? aga[i] : (pass == 1 ? agb[i] : adx[i]);
       *reinterpret_cast<float4*>(r1s + slot * c + 4 * (sub + i * L)) = pass == 0 ? aba[i] : abb[i];
     }
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += kLnThreads) {
       float t0 = 0.f, t1 = 0.f;
       for (int sl = 0; sl < slots; ++sl) { t0 += r0s[sl * c + ch]; t1 += r1s[sl * c + ch]; }
-      a.part[((int64_t)blockIdx.x * 4 + 2 * pass) * c + ch] = t0;
-      a.part[((int64_t)blockIdx.x * 4 + 2 * pass + 1) * c + ch] = t1;
+      if (pass < 2) {
+        a.part[((int64_t)blockIdx.x * 5 + 2 * pass) * c + ch] = t0;
+        a.part[((int64_t)blockIdx.x * 5 + 2 * pass + 1) * c + ch] = t1;
+      } else {
+        a.part[((int64_t)blockIdx.x * 5 + 4) * c + ch] = t0;
+      }
     }
   }
 }
@@ -262,15 +272,15 @@ fused_residual_bwd_kernel(FusedResBwdArgs a) {
 // out[v][ch] = sum_b part[b][v][ch] for the parameter vectors v whose destination pointer is non-null; block = 32 channels
 __global__ void __launch_bounds__(256)
 fused_param_reduce_kernel(const float* __restrict__ part, int blocks, int c, float* __restrict__ o0, float* __restrict__ o1,
-                          float* __restrict__ o2, float* __restrict__ o3) {
+                          float* __restrict__ o2, float* __restrict__ o3, float* __restrict__ o4) {
   __shared__ float sm[8][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane;
-  float* outs[4] = {o0, o1, o2, o3};
-  for (int v = 0; v < 4; ++v) {
+  float* outs[5] = {o0, o1, o2, o3, o4};
+  for (int v = 0; v < 5; ++v) {
     if (!outs[v]) continue;
     float acc = 0.f;
-    for (int b = grp; b < blocks; b += 8) acc += part[((int64_t)b * 4 + v) * c + ch];
+    for (int b = grp; b < blocks; b += 8) acc += part[((int64_t)b * 5 + v) * c + ch];
     __syncthreads();
     sm[grp][lane] = acc;
     __syncthreads();
@@ -284,7 +294,7 @@ fused_param_reduce_kernel(const float* __restrict__ part, int blocks, int c, flo
 }
 
 inline bool fused_channels_ok(int c) { return c == 32 || c == 64 || c == 128 || c == 256 || c == 512; }
-inline size_t fused_residual_bwd_workspace_bytes(int64_t n, int c) { return (size_t)ln_blocks(n) * 4 * c * sizeof(float) + 256; }
+inline size_t fused_residual_bwd_workspace_bytes(int64_t n, int c) { return (size_t)ln_blocks(n) * 5 * c * sizeof(float) + 256; }
 
 #define B2PC_FR_DISPATCH(DT, VV, KERNEL, ...)                                                          \
   do {                                                                                                 \
@@ -308,9 +318,10 @@ inline int launch_fused_residual_fwd(const FusedResArgs& a, int dtype, cudaStrea
   return B2PC_OK;
 }
 
-inline int launch_fused_residual_bwd(const FusedResBwdArgs& a0, int dtype, float* dga, float* dba, float* dgb, float* dbb, void* ws,
-                                     size_t ws_bytes, cudaStream_t stream) {
+inline int launch_fused_residual_bwd(const FusedResBwdArgs& a0, int dtype, float* dga, float* dba, float* dgb, float* dbb, float* dx_colsum,
+                                     void* ws, size_t ws_bytes, cudaStream_t stream) {
   FusedResBwdArgs a = a0;
+  a.want_dx_colsum = dx_colsum != nullptr;
   B2PC_CHECK_ARG(fused_channels_ok(a.c), "fused_residual: channels %d not one of 32/64/128/256/512", a.c);
   B2PC_CHECK_ARG(dtype == B2PC_F32 || dtype == B2PC_F16 || dtype == B2PC_BF16, "fused_residual: bad dtype %d", dtype);
   B2PC_CHECK_ARG(a.d_shortcut && a.dx && ws, "fused_residual_bwd: null pointer");
@@ -322,7 +333,7 @@ inline int launch_fused_residual_bwd(const FusedResBwdArgs& a0, int dtype, float
     if (dbb) cudaMemsetAsync(dbb, 0, a.c * sizeof(float), stream);
   }
   if (a.n == 0) {
-    float* outs[4] = {ln_a ? dga : nullptr, ln_a ? dba : nullptr, ln_b ? dgb : nullptr, ln_b ? dbb : nullptr};
+    float* outs[5] = {ln_a ? dga : nullptr, ln_a ? dba : nullptr, ln_b ? dgb : nullptr, ln_b ? dbb : nullptr, dx_colsum};
     for (float* o : outs) if (o) cudaMemsetAsync(o, 0, a.c * sizeof(float), stream);
     return B2PC_OK;
   }
@@ -333,9 +344,9 @@ inline int launch_fused_residual_bwd(const FusedResBwdArgs& a0, int dtype, float
   const int blocks = ln_blocks(a.n);
   B2PC_FR_DISPATCH(dtype, vv, fused_residual_bwd_kernel, <<<blocks, kLnThreads, smem, stream>>>(a));
   count_launches(1);
-  if (ln_a || ln_b) {
+  if (ln_a || ln_b || dx_colsum) {
     fused_param_reduce_kernel<<<a.c / 32, 256, 0, stream>>>(a.part, blocks, a.c, ln_a ? dga : nullptr, ln_a ? dba : nullptr,
-                                                            ln_b ? dgb : nullptr, ln_b ? dbb : nullptr);
+                                                            ln_b ? dgb : nullptr, ln_b ? dbb : nullptr, dx_colsum);
     count_launches(1);
   }
   B2PC_CHECK_LAUNCH("fused_residual_bwd");

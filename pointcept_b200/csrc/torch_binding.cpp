@@ -374,7 +374,9 @@ struct FusedResidualFn : public torch::autograd::Function<FusedResidualFn> {
   // returns {r} + ({r16} if emit_half) + ({y} if LayerNorm_b); flags are recoverable from the argument list
   static variable_list forward(AutogradContext* ctx, Tensor shortcut, Tensor x, c10::optional<Tensor> u, double keep,
                                c10::optional<Tensor> ga, c10::optional<Tensor> ba, double eps_a, c10::optional<Tensor> gb,
-                               c10::optional<Tensor> bb, double eps_b, bool emit_half) {
+                               c10::optional<Tensor> bb, double eps_b, bool emit_half, c10::optional<Tensor> x_bias) {
+    // x_bias: the bias parameter of the Linear that produced x (already added there); it only routes its gradient -- the
+    // column sums of dx -- through this node, so that Linear needs no separate bias-gradient reduction
     B2PC_GUARD(x);
     TORCH_CHECK(shortcut.scalar_type() == at::kFloat, "fused_residual: the residual stream is fp32");
     shortcut = shortcut.contiguous();
@@ -397,6 +399,7 @@ struct FusedResidualFn : public torch::autograd::Function<FusedResidualFn> {
     ctx->saved_data["emit_half"] = emit_half;
     ctx->saved_data["has_ba"] = baf.defined();
     ctx->saved_data["has_bb"] = bbf.defined();
+    ctx->saved_data["xb_dtype"] = (x_bias.has_value() && x_bias->defined()) ? (int64_t)x_bias->scalar_type() : (int64_t)-1;
     variable_list outs{r};
     if (emit_half) outs.push_back(r16);
     if (y.defined()) outs.push_back(y);
@@ -420,16 +423,20 @@ struct FusedResidualFn : public torch::autograd::Function<FusedResidualFn> {
     Tensor dga, dba, dgb, dbb;
     if (gaf.defined()) { dga = at::empty({c}, r.options()); dba = at::empty({c}, r.options()); }
     if (gbf.defined()) { dgb = at::empty({c}, r.options()); dbb = at::empty({c}, r.options()); }
+    const int64_t xbd = ctx->saved_data["xb_dtype"].toInt();
+    Tensor dxb = (xbd >= 0 && ctx->needs_input_grad(11)) ? at::empty({c}, r.options()) : Tensor();
     Tensor ws = workspace(b2pc_fused_residual_bwd_workspace_bytes(n, (int)c), x);
     check(b2pc_fused_residual_bwd(fptr(dr_out), optr(dr16), optr(dy), dt(x), r.data_ptr<float>(), x.data_ptr(), fptr(uf),
                                   (float)ctx->saved_data["keep"].toDouble(), fptr(gaf), fptr(gbf), fptr(sa), fptr(sb), n, (int)c,
                                   d_shortcut.data_ptr<float>(), dx.data_ptr(), dga.defined() ? dga.data_ptr<float>() : nullptr,
                                   dba.defined() ? dba.data_ptr<float>() : nullptr, dgb.defined() ? dgb.data_ptr<float>() : nullptr,
-                                  dbb.defined() ? dbb.data_ptr<float>() : nullptr, ws.data_ptr(), (size_t)ws.numel(), cur_stream()),
+                                  dbb.defined() ? dbb.data_ptr<float>() : nullptr, dxb.defined() ? dxb.data_ptr<float>() : nullptr, ws.data_ptr(),
+                                  (size_t)ws.numel(), cur_stream()),
           "fused_residual_bwd");
     if (!ctx->saved_data["has_ba"].toBool()) dba = Tensor();
     if (!ctx->saved_data["has_bb"].toBool()) dbb = Tensor();
-    return {d_shortcut, dx, Tensor(), Tensor(), dga, dba, Tensor(), dgb, dbb, Tensor(), Tensor()};
+    if (dxb.defined() && (at::ScalarType)xbd != at::kFloat) dxb = dxb.to((at::ScalarType)xbd);
+    return {d_shortcut, dx, Tensor(), Tensor(), dga, dba, Tensor(), dgb, dbb, Tensor(), Tensor(), dxb};
   }
 };
 
@@ -527,8 +534,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return LinearFn::apply(x, w, b, ccode, w16, b16);
   }, py::arg("x"), py::arg("weight"), py::arg("bias"), py::arg("ccode"), py::arg("w16") = py::none(), py::arg("b16") = py::none());
   m.def("fused_residual", [](Tensor shortcut, Tensor x, c10::optional<Tensor> u, double keep, c10::optional<Tensor> ga, c10::optional<Tensor> ba,
-                             double eps_a, c10::optional<Tensor> gb, c10::optional<Tensor> bb, double eps_b, bool emit_half) {
-    return FusedResidualFn::apply(shortcut, x, u, keep, ga, ba, eps_a, gb, bb, eps_b, emit_half);
+                             double eps_a, c10::optional<Tensor> gb, c10::optional<Tensor> bb, double eps_b, bool emit_half,
+                             c10::optional<Tensor> x_bias) {
+    return FusedResidualFn::apply(shortcut, x, u, keep, ga, ba, eps_a, gb, bb, eps_b, emit_half, x_bias);
   });
   m.def("gelu", [](Tensor x) { return GeluFn::apply(x); });
   m.def("serialized_attention", [](Tensor qkv, Tensor gidx, Tensor sidx, Tensor dup_point, Tensor cu, int64_t max_seqlen, int64_t heads,

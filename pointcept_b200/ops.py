@@ -552,15 +552,17 @@ def linear(x, weight, bias, w16=None, b16=None):
     return torch.nn.functional.linear(x, weight, bias)
 
 
-def fused_residual(shortcut, x, u=None, keep=1.0, ln_a=None, ln_b=None, emit_half=False):
+def fused_residual(shortcut, x, u=None, keep=1.0, ln_a=None, ln_b=None, emit_half=False, x_bias=None):
     """csrc/fused.cuh through the compiled binding: r = shortcut + dropscale * [LN_a](x); optional half copy of r; optional
-    y = LN_b(r) in x's dtype.  ln_a / ln_b: nn.LayerNorm modules or None.  Returns (r, r16 or None, y or None)."""
+    y = LN_b(r) in x's dtype.  ln_a / ln_b: nn.LayerNorm modules or None.  Returns (r, r16 or None, y or None).
+    x_bias: bias parameter of the Linear that produced x when that Linear was called with the bias detached -- its gradient
+    (column sums of dx) is then produced by this node's backward instead of a separate reduction."""
     B = binding()
     assert B is not None, "fused_residual needs the compiled binding"
     outs = B.fused_residual(shortcut, x, u, float(keep),
                             None if ln_a is None else ln_a.weight, None if ln_a is None else ln_a.bias, 1e-5 if ln_a is None else ln_a.eps,
                             None if ln_b is None else ln_b.weight, None if ln_b is None else ln_b.bias, 1e-5 if ln_b is None else ln_b.eps,
-                            bool(emit_half))
+                            bool(emit_half), x_bias)
     r = outs[0]
     r16 = outs[1] if emit_half else None
     y = outs[-1] if ln_b is not None else None

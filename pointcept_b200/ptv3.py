@@ -56,7 +56,9 @@ class FusedLinear(nn.Linear):
     use_fused_bias_grad = None   # None: on exactly when the compiled binding is present (its C++ node is cheaper than autograd's)
     _b2pc_half_shadow = True     # ops.HalfShadows keeps half-precision copies of weight / bias for the autocast path
 
-    def forward(self, x):
+    def forward(self, x, bias_grad_elsewhere=False):
+        """bias_grad_elsewhere: the caller routes the bias gradient through the fused residual kernel that consumes this
+        layer's output (ops.fused_residual(..., x_bias=self.bias)); the bias then enters detached here."""
         on = FusedLinear.use_fused_bias_grad
         if on is None:
             on = ops.binding() is not None
@@ -64,7 +66,9 @@ class FusedLinear(nn.Linear):
             w16 = b16 = None
             if torch.is_autocast_enabled():
                 w16, b16 = ops.shadow_of(self, torch.get_autocast_dtype("cuda"))
-            return ops.linear(x, self.weight, self.bias, w16, b16)
+            bias = self.bias.detach() if (bias_grad_elsewhere and self.bias is not None) else self.bias
+            return ops.linear(x, self.weight, bias, w16, b16)
+        assert not bias_grad_elsewhere
         return nn.functional.linear(x, self.weight, self.bias)
 
 
@@ -188,16 +192,17 @@ class SerializedAttention(PointModule):
             point[key] = (gidx, sidx, dup_points.int())
         return point[key]
 
-    def forward(self, point):
+    def forward(self, point, proj_bias_grad_elsewhere=False):
         H, K, C = self.num_heads, self.patch_size, self.channels
         _, _, cu_seqlens = self.get_padding_and_inverse(point)
         B = ops.binding()
+        ext = proj_bias_grad_elsewhere and self.proj_drop.p == 0.0
         if B is not None and SerializedAttention.fused and C // H == 16 and ops.get_impl() != 1 and point.feat.is_cuda:
             gidx, sidx, dup_point = self._fused_tables(point)
             qkv = self.qkv(point.feat)
             # bf16 at the operator boundary whatever the autocast dtype, exactly as the reference (ptv3m1:209)
             feat = B.serialized_attention(qkv.to(torch.bfloat16), gidx, sidx, dup_point, cu_seqlens, K, H, float(self.scale)).to(qkv.dtype)
-            point.feat = self.proj_drop(self.proj(feat))
+            point.feat = self.proj(feat, bias_grad_elsewhere=True) if ext else self.proj_drop(self.proj(feat))
             return point
         order_pad, primary_pos, dup_slots, dup_points = self._gather_indices(point)
         qkv = serialized_gather(self.qkv(point.feat), order_pad, primary_pos, None, K, dup=(dup_slots, dup_points))
@@ -205,7 +210,7 @@ class SerializedAttention(PointModule):
         feat = flash_attn_varlen_qkvpacked_func(qkv.to(torch.bfloat16).reshape(-1, 3, H, C // H), cu_seqlens, max_seqlen=K,
                                                 softmax_scale=self.scale).reshape(-1, C)
         feat = serialized_scatter_back(feat.to(qkv.dtype), primary_pos)
-        point.feat = self.proj_drop(self.proj(feat))
+        point.feat = self.proj(feat, bias_grad_elsewhere=True) if ext else self.proj_drop(self.proj(feat))
         return point
 
 
@@ -219,9 +224,11 @@ class MLP(nn.Module):
         self.fc2 = FusedLinear(hidden_channels, out_channels)
         self.drop = nn.Dropout(drop)
 
-    def forward(self, x):
+    def forward(self, x, fc2_bias_grad_elsewhere=False):
         h = self.fc1(x)
         h = ops.gelu(h) if (type(self.act) is nn.GELU and self.act.approximate == "none") else self.act(h)
+        if fc2_bias_grad_elsewhere and self.drop.p == 0.0:
+            return self.fc2(h, bias_grad_elsewhere=True)
         return self.drop(self.fc2(self.drop(h)))
 
 
@@ -277,16 +284,19 @@ class Block(PointModule):
         if r0.dtype != torch.float32:
             r0 = r0.float()
         n, dev = r0.shape[0], r0.device
+        # the three Linears whose outputs feed a fused residual kernel get their bias gradients from that kernel's backward
+        # (column sums of dx) instead of a reduction of their own
+        ext = self.attn.proj_drop.p == 0.0 and self.mlp[0].drop.p == 0.0 and isinstance(self.cpe[1], FusedLinear)
         sct = self.cpe[0](point.sparse_conv_feat)
-        lin = self.cpe[1](sct.features)
-        r1, _, y1 = ops.fused_residual(r0, lin, None, 1.0, self.cpe[2], self.norm1[0], False)
+        lin = self.cpe[1](sct.features, bias_grad_elsewhere=ext)
+        r1, _, y1 = ops.fused_residual(r0, lin, None, 1.0, self.cpe[2], self.norm1[0], False, self.cpe[1].bias if ext else None)
         point.feat = y1
-        point = self.attn(point)
+        point = self.attn(point, proj_bias_grad_elsewhere=ext)
         u, keep = self._drop_rand(point, n, dev)
-        r2, _, y2 = ops.fused_residual(r1, point.feat, u, keep, None, self.norm2[0], False)
-        m = self.mlp[0](y2)
+        r2, _, y2 = ops.fused_residual(r1, point.feat, u, keep, None, self.norm2[0], False, self.attn.proj.bias if ext else None)
+        m = self.mlp[0](y2, fc2_bias_grad_elsewhere=ext)
         u, keep = self._drop_rand(point, n, dev)
-        r3, r16, _ = ops.fused_residual(r2, m, u, keep, None, None, amp and m.dtype != torch.float32)
+        r3, r16, _ = ops.fused_residual(r2, m, u, keep, None, None, amp and m.dtype != torch.float32, self.mlp[0].fc2.bias if ext else None)
         point.feat = r3
         point.sparse_conv_feat = sct.replace_feature(r3)
         if r16 is not None:

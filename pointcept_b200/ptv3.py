@@ -8,6 +8,7 @@ the reference's per-scene python loop; pooling clusters come from the already-so
 instead of torch.unique + torch.sort.
 """
 import math
+import os
 from functools import partial
 
 import torch
@@ -176,7 +177,8 @@ class SerializedAttention(PointModule):
             point[key] = (order_pad, primary_pos, dup_slots, order_pad[dup_slots])
         return point[key]
 
-    fused = True   # class switch: gather-fused serialized attention (one operator) when the compiled binding + tcgen05 path apply
+    # class switch: gather-fused serialized attention (one operator) when the compiled binding + tcgen05 path apply
+    fused = os.environ.get("B2PC_ATTN_FUSED", "1") != "0"
 
     @torch.no_grad()
     def _fused_tables(self, point):
@@ -259,7 +261,8 @@ class Block(PointModule):
                 if isinstance(seq[0], FusedLayerNorm):
                     seq[0].emit_autocast_dtype = True
 
-    fused = True   # class switch: one fused residual kernel per sub-layer (csrc/fused.cuh) when the compiled binding is present
+    # class switch: one fused residual kernel per sub-layer (csrc/fused.cuh) when the compiled binding is present
+    fused = os.environ.get("B2PC_BLOCK_FUSED", "1") != "0"
 
     def _drop_rand(self, point, n, dev):
         """uniform randoms for DropPath (one per row), sliced from a pool filled by a single torch.rand per forward"""

@@ -88,6 +88,14 @@ class SpUNetBase(nn.Module):
             nn.init.constant_(m.weight, 1.0)
 
     def forward(self, input_dict):
+        if torch.is_autocast_enabled() and input_dict["feat"].is_cuda:
+            from . import ops
+            if ops.binding() is not None:      # one launch refreshes the half-precision shadows of every conv weight
+                sh = self.__dict__.get("_half_shadows")
+                if sh is None:
+                    sh = ops.HalfShadows(self)
+                    self.__dict__["_half_shadows"] = sh
+                sh.sync(torch.get_autocast_dtype("cuda"))
         grid_coord, feat, offset = input_dict["grid_coord"], input_dict["feat"], input_dict["offset"]
         if "offset_host" in input_dict:
             oh = input_dict["offset_host"]

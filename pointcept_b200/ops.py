@@ -77,10 +77,19 @@ def _stream():
 
 
 def _need_cuda(*ts):
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("pointcept_b200 operators run on CUDA tensors only (got a %s tensor); "
                                "there is no CPU fallback" % t.device.type)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the ctypes binding launches on the CURRENT device's stream; the compiled binding pins the tensor's device itself
+            raise RuntimeError(f"ctypes binding: tensor on cuda:{t.device.index} but the current device is cuda:{cur}; wrap the call in "
+                               "`with torch.cuda.device_of(tensor):` (or use the compiled binding, which guards the device itself)")
 
 
 def _p(t):

@@ -366,26 +366,33 @@ inline int launch_attn_fwd_umma(const void* qkv, int dtype, const int32_t* cu, i
 // The same shared-memory bytes serve as K-major operand (rows x 16 channels) and as MN-major operand (16 channels x rows):
 // only the descriptor differs.
 constexpr int kAbK = 128;   // keys per CTA (= threads)
-constexpr int kAbQ = 64;    // queries per sweep step
 constexpr int kAbStages = 3;
-constexpr int kAbTmemCols = 256;
-// smem: K_j 4096 | V_j 4096 | dS (A of the dQ MMA) 64x128x2 = 16384 | stages x (Q 2048 | dO 2048 | lse2 256 | delta 256) | bar, slot
-constexpr int kAbStageBytes = 2048 + 2048 + 256 + 256;
-constexpr int kAbSmemBytes = 4096 + 4096 + 16384 + kAbStages * kAbStageBytes + 64;
+// BQ = queries per sweep step.  BQ = 64: 256 TMEM columns (S 64 | dP 64 | P 32 | dS 32 | dV dK dQ 48) -> 2 CTAs per SM.
+// BQ = 32: P overwrites the S columns and dS the dP columns once a thread holds its row of both in registers (TMEM lanes are
+// private to their thread), so 128 columns suffice (S/P 32 | dP/dS 32 | dV dK dQ 48) and FOUR CTAs share an SM: the kernel is
+// bound by the latency of its issue -> commit -> wait -> softmax -> barrier chain (ncu: barrier + wait stalls dominate, XU pipe
+// 27 %), which twice as many resident CTAs hide.  The dQ MMA keeps M = 64 (upper 32 rows of its operand are zero planes).
+// smem: K_j 4096 | V_j 4096 | dS (A of the dQ MMA) 64x128x2 = 16384 | stages x (Q BQ*32 | dO BQ*32 | lse2 BQ*4 | delta BQ*4) | bar, slot
+template <int BQ> __host__ __device__ constexpr int attn_bwd_stage_bytes() { return BQ * 32 + BQ * 32 + BQ * 4 + BQ * 4; }
+template <int BQ> __host__ __device__ constexpr int attn_bwd_smem_bytes() { return 4096 + 4096 + 16384 + kAbStages * attn_bwd_stage_bytes<BQ>() + 64; }
+template <int BQ> __host__ __device__ constexpr int attn_bwd_tmem_cols() { return BQ == 64 ? 256 : 128; }
 
 // GATHER = true: serialized mode (see the forward kernel): qkv / dout / dqkv hold POINT rows; slot t reads point row gidx[t],
 // its dO is dout[sidx[t]] when sidx[t] >= 0 and zero otherwise (the output of a borrowed filler slot was dropped); dK / dV of a
 // primary slot go straight to the point's row of dqkv, those of filler slot with sidx = -(r+1) to row r of `side` [n_dup, 2, H, 16]
 // (added to the point's row afterwards: a point owns at most one filler slot besides its primary one).
-template <typename T, bool GATHER>
-__global__ void __launch_bounds__(kAbK)
+template <typename T, bool GATHER, int BQ>
+__global__ void __launch_bounds__(kAbK, BQ == 32 ? 4 : 2)
 attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, const float* __restrict__ lse,
                      const float* __restrict__ delta, const int32_t* __restrict__ cu, int64_t t_total, int H, float scale,
                      T* __restrict__ dqkv, float* __restrict__ dq_acc, const int32_t* __restrict__ gidx,
                      const int32_t* __restrict__ sidx, T* __restrict__ side) {
   using namespace umma;
   constexpr int D = 16;
-  constexpr uint32_t COL_S = 0, COL_DP = 64, COL_P = 128, COL_DS = 160, COL_DV = 192, COL_DK = 208, COL_DQ = 224;
+  static_assert(BQ == 32 || BQ == 64, "query block");
+  constexpr int kAbQ = BQ, kAbStageBytes = attn_bwd_stage_bytes<BQ>(), kAbTmemCols = attn_bwd_tmem_cols<BQ>();
+  constexpr uint32_t COL_S = 0, COL_DP = BQ, COL_P = BQ == 64 ? 128 : 0, COL_DS = BQ == 64 ? 160 : BQ,
+                     COL_DV = BQ == 64 ? 192 : 64, COL_DK = COL_DV + 16, COL_DQ = COL_DV + 32;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* k_s = smem;
   uint8_t* v_s = smem + 4096;
@@ -428,30 +435,34 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   auto load_q = [&](int blk, int stage) {
     uint8_t* st = st_s + stage * kAbStageBytes;
     const int q0 = blk * kAbQ;
-    {  // 64 rows x 2 chunks of Q and of dO = 256 pieces: thread -> (which, row, chunk)
+    if ((tid & 63) < kAbQ) {  // BQ rows x 2 chunks of Q and of dO: thread -> (which, row)
       const int which = tid >> 6, r = (tid & 63);
       const bool ok = q0 + r < len;
       if (which == 0) {
         const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(gix + q0 + r) : 0) : (int64_t)(q0 + r);
         const T* src = base_q + prow * row_stride;
         cp_async16(smem_u32(st + r * 16), ok ? src : base_q, ok);
-        cp_async16(smem_u32(st + 1024 + r * 16), ok ? src + 8 : base_q, ok);
+        cp_async16(smem_u32(st + kAbQ * 16 + r * 16), ok ? src + 8 : base_q, ok);
       } else {
         const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(six + q0 + r) : -1) : (int64_t)(q0 + r);
         const bool okd = ok && prow >= 0;
         const T* src = base_do + (okd ? prow : 0) * (H * D);
-        cp_async16(smem_u32(st + 2048 + r * 16), src, okd);
-        cp_async16(smem_u32(st + 2048 + 1024 + r * 16), src + 8, okd);
+        cp_async16(smem_u32(st + kAbQ * 32 + r * 16), src, okd);
+        cp_async16(smem_u32(st + kAbQ * 32 + kAbQ * 16 + r * 16), src + 8, okd);
       }
-      // lse / delta of the 64 queries (4-byte async copies; zero when the query does not exist)
+      // lse / delta of the BQ queries (4-byte async copies; zero when the query does not exist)
       const float* g = (which == 0 ? base_lse : base_dl) + q0 + r;
-      cp_async4(smem_u32(st + 4096 + which * 256 + r * 4), ok ? g : base_lse, ok);
+      cp_async4(smem_u32(st + kAbQ * 64 + which * (kAbQ * 4) + r * 4), ok ? g : base_lse, ok);
     }
   };
   load_q(0, 0);
   cp_async_commit();
   if (nblk > 1) load_q(1, 1);
   cp_async_commit();
+  if (kAbQ < 64) {   // the dQ MMA has M = 64: the query rows this kernel never fills are zero planes of its A operand
+    for (int q = tid; q < (64 - kAbQ) * 128 * 2 / 16; q += kAbK) reinterpret_cast<uint4*>(ds_s + kAbQ * 256)[q] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -473,7 +484,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
     tmem_ld16(lane_base + COL_DQ, r);
     tmem_ld_wait();
     const int qi = blk * kAbQ + warp * 16 + lane;
-    if (lane < 16 && qi < len) {
+    if (lane < 16 && warp * 16 < kAbQ && qi < len) {
       float* dst = dq_acc + ((s0 + qi) * H + h) * D;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -491,7 +502,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
     if (tid == 0) {
       tc_fence_after();
       mma_ss(tmem_base + COL_S, desc_k, make_smem_desc(smem_u32(st), kAbQ * 16, 128), idesc_s, 0);
-      mma_ss(tmem_base + COL_DP, desc_v, make_smem_desc(smem_u32(st + 2048), kAbQ * 16, 128), idesc_s, 0);
+      mma_ss(tmem_base + COL_DP, desc_v, make_smem_desc(smem_u32(st + kAbQ * 32), kAbQ * 16, 128), idesc_s, 0);
       mma_commit(bar);
     }
     mbar_wait(bar, i & 1);
@@ -499,8 +510,8 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
     if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages);
     cp_async_commit();
     if (i > 0) flush_dq(i - 1);
-    const float* lse_s = reinterpret_cast<const float*>(st + 4096);
-    const float* dl_s = reinterpret_cast<const float*>(st + 4096 + 256);
+    const float* lse_s = reinterpret_cast<const float*>(st + kAbQ * 64);
+    const float* dl_s = reinterpret_cast<const float*>(st + kAbQ * 64 + kAbQ * 4);
 #pragma unroll
     for (int ch = 0; ch < kAbQ / 32; ++ch) {
       uint32_t s_r[32], dp_r[32];
@@ -551,7 +562,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < kAbQ / 16; ++ks) {   // reduction over the 64 queries, 16 per MMA
-        mma_ts(tmem_base + COL_DV, tmem_base + COL_P + ks * 8, make_smem_desc(smem_u32(st + 2048 + ks * 256), 128, kAbQ * 16),
+        mma_ts(tmem_base + COL_DV, tmem_base + COL_P + ks * 8, make_smem_desc(smem_u32(st + kAbQ * 32 + ks * 256), 128, kAbQ * 16),
                idesc_kv, (i > 0 || ks > 0) ? 1u : 0u);
         mma_ts(tmem_base + COL_DK, tmem_base + COL_DS + ks * 8, make_smem_desc(smem_u32(st + ks * 256), 128, kAbQ * 16), idesc_kv,
                (i > 0 || ks > 0) ? 1u : 0u);
@@ -695,15 +706,16 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
   attn_bwd_prep_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>((const T*)dout, (const T*)out, lse, t, H, delta, nlse2, sidx);
   cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
   dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
-  if (gidx) {
-    cudaFuncSetAttribute(attn_bwd_umma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
-    attn_bwd_umma_kernel<T, true><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, scale, (T*)dqkv,
-                                                                        dq_acc, gidx, sidx, side);
-  } else {
-    cudaFuncSetAttribute(attn_bwd_umma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
-    attn_bwd_umma_kernel<T, false><<<grid, kAbK, kAbSmemBytes, stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, scale, (T*)dqkv,
-                                                                         dq_acc, nullptr, nullptr, nullptr);
-  }
+  static const int bq = [] { const char* e = getenv("B2PC_ATTN_BQ"); return (e && atoi(e) == 64) ? 64 : 32; }();
+#define B2PC_ATTN_BWD_LAUNCH(G, Q)                                                                                                       \
+  do {                                                                                                                                   \
+    cudaFuncSetAttribute(attn_bwd_umma_kernel<T, G, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes<Q>());          \
+    attn_bwd_umma_kernel<T, G, Q><<<grid, kAbK, attn_bwd_smem_bytes<Q>(), stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, \
+                                                                                   scale, (T*)dqkv, dq_acc, gidx, sidx, side);           \
+  } while (0)
+  if (gidx) { if (bq == 64) B2PC_ATTN_BWD_LAUNCH(true, 64); else B2PC_ATTN_BWD_LAUNCH(true, 32); }
+  else { if (bq == 64) B2PC_ATTN_BWD_LAUNCH(false, 64); else B2PC_ATTN_BWD_LAUNCH(false, 32); }
+#undef B2PC_ATTN_BWD_LAUNCH
   attn_dq_finish_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>(dq_acc, t * H, H, scale, (T*)dqkv, sidx);
   count_launches(3);
   if (gidx && n_dup > 0) {

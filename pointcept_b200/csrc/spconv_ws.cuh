@@ -43,21 +43,22 @@ __device__ __forceinline__ uint32_t ld_shared_volatile_u32(const uint32_t* p) {
 }
 
 constexpr int kWsRows = 128;        // output rows per tile (= TMEM lanes)
-constexpr int kWsThreads = 288;     // warps 0-3 epilogue, warps 4-7 producers, warp 8 MMA
+constexpr int kWsThreads = 288;     // warps 0-3 epilogue, warps 4-7 producers (thread = row), warp 8 MMA
 constexpr int kWsMaxStages = 16;
 constexpr int kWsCtrlBytes = 512;   // barriers + bookkeeping at the start of dynamic shared memory
 constexpr int kWsSmemBudget = 200 * 1024;
-constexpr uint32_t kMetaFirst = 1u << 20, kMetaEnd = 1u << 21;
+constexpr int kWsMaxKV = 128;       // kernel volume limit of this path (125 = 5^3 stem)
+constexpr uint32_t kMetaEnd = 1u << 21;
 
 struct ConvWsCfg {
-  int kc, n_cc, n_tile, n_ntiles, stages, lag, tmem_cols, w_resident, a_bytes, b_bytes, stage_bytes, res_bytes, smem_bytes, grid;
+  int kc, n_cc, n_tile, n_ntiles, stages, lag, tmem_cols, w_resident, a_bytes, b_bytes, stage_bytes, res_bytes, idx_bytes, smem_bytes, grid;
   long long n_items;
 };
 
 inline bool conv_ws_supported(int dtype, int c_in, int c_out, int kv) {
   if (dtype != B2PC_F16 && dtype != B2PC_BF16) return false;
   if (c_in % 16 != 0 || c_out % 16 != 0) return false;
-  if (kv > 343) return false;
+  if (kv > kWsMaxKV) return false;
   return true;
 }
 
@@ -71,29 +72,28 @@ inline ConvWsCfg conv_ws_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   int best = 0;
   for (int nt = c_out <= 256 ? c_out : 256; nt >= 16; nt -= 16) {
     if (c_out % nt != 0) continue;
-    if (best == 0) best = nt;
-    if (m_tiles * (c_out / nt) >= kNumSMs) { best = nt; break; }
-    best = nt;   // keeps shrinking while the grid is under-filled
-    if (nt <= 32) break;
+    best = nt;
+    if (m_tiles * (c_out / nt) >= kNumSMs || nt <= 32) break;
   }
   c.n_tile = best;
   c.n_ntiles = c_out / c.n_tile;
   c.n_items = m_tiles * c.n_ntiles;
   c.a_bytes = kWsRows * c.kc * 2;
   c.b_bytes = c.n_tile * c.kc * 2;
+  c.idx_bytes = 2 * kv * kWsRows * 4 + 2 * kWsMaxKV;       // two rulebook-slice buffers + two active-offset lists
   const long long res = (long long)kv * c.n_cc * c.b_bytes;
-  c.w_resident = (c.n_ntiles == 1 && res <= 132 * 1024) ? 1 : 0;
+  const long long avail = kWsSmemBudget - kWsCtrlBytes - c.idx_bytes;
+  c.w_resident = (c.n_ntiles == 1 && res + 8 * c.a_bytes <= avail) ? 1 : 0;
   c.res_bytes = c.w_resident ? (int)res : 0;
   c.stage_bytes = c.a_bytes + (c.w_resident ? 0 : c.b_bytes);
-  int st = (kWsSmemBudget - kWsCtrlBytes - c.res_bytes) / c.stage_bytes;
+  int st = (int)((avail - c.res_bytes) / c.stage_bytes);
   if (st > kWsMaxStages) st = kWsMaxStages;
   if (st < 3) st = 3;
   c.stages = st;
-  c.lag = st - 2 > 12 ? 12 : st - 2;
-  if (c.lag < 1) c.lag = 1;
+  c.lag = st >= 8 ? 6 : 2;
   c.tmem_cols = 32;
   while (c.tmem_cols < 2 * c.n_tile) c.tmem_cols <<= 1;
-  c.smem_bytes = kWsCtrlBytes + c.res_bytes + c.stages * c.stage_bytes;
+  c.smem_bytes = kWsCtrlBytes + c.idx_bytes + c.res_bytes + c.stages * c.stage_bytes;
   c.grid = (int)(c.n_items < kNumSMs ? c.n_items : kNumSMs);
   return c;
 }
@@ -104,12 +104,16 @@ struct WsCtrl {            // lives at the start of dynamic smem
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t meta[kWsMaxStages];
-  uint32_t mask_x[4];
+  uint32_t mask_x[3][4];
   uint32_t tmem_slot;
 };
 static_assert(sizeof(WsCtrl) <= kWsCtrlBytes, "control block too large");
 
-template <typename T, int KC>
+// Producer threads own one output row each (128 rows = 4 warps) and copy that row's KC channels of every active kernel offset with
+// KC/8 cp.async from ONE base pointer -- the leanest instruction stream per gathered byte, which is what bounds this kernel
+// (ncu: with one warp per scheduler the producers are issue-latency bound).  The rulebook slice of the NEXT tile is fetched by
+// 4-byte cp.async into a second shared-memory buffer while the current tile's rows stream, so no index load is ever exposed.
+template <typename T, int KC, int LAG>
 __global__ void __launch_bounds__(kWsThreads, 1)
 conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
@@ -117,21 +121,22 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
   using namespace umma;
   extern __shared__ __align__(128) uint8_t smem[];
   WsCtrl* ctl = reinterpret_cast<WsCtrl*>(smem);
-  uint8_t* w_res = smem + kWsCtrlBytes;
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem + kWsCtrlBytes);                       // [2][kv][128]
+  uint8_t* act_s = smem + kWsCtrlBytes + 2 * kv * kWsRows * 4;                            // [2][kWsMaxKV]
+  uint8_t* w_res = smem + kWsCtrlBytes + cfg.idx_bytes;
   uint8_t* ring = w_res + cfg.res_bytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = cfg.stages, LAG = cfg.lag, n_tile = cfg.n_tile, n_cc = cfg.n_cc, n_ntiles = cfg.n_ntiles;
+  const int S = cfg.stages, n_tile = cfg.n_tile, n_cc = cfg.n_cc, n_ntiles = cfg.n_ntiles;
   const int a_bytes = cfg.a_bytes, b_bytes = cfg.b_bytes, stage_bytes = cfg.stage_bytes;
   const bool resident = cfg.w_resident != 0;
   const long long n_items = cfg.n_items;
-  constexpr int LPR = KC / 8;      // lanes (16-byte pieces) per gathered row
-  constexpr int RPI = 32 / LPR;    // rows per warp instruction
+  constexpr int LPR = KC / 8;      // 16-byte pieces per gathered row
 
   if (warp == 0) { tmem_alloc(&ctl->tmem_slot, cfg.tmem_cols); tmem_relinquish(); }
   if (tid == 32) {
     for (int s = 0; s < S; ++s) { mbar_init(&ctl->full[s], 128); mbar_init(&ctl->empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&ctl->acc_full[b], 1); mbar_init(&ctl->acc_empty[b], 128); }
-    ctl->mask_x[0] = ctl->mask_x[1] = ctl->mask_x[2] = 0;
+    for (int i = 0; i < 12; ++i) (&ctl->mask_x[0][0])[i] = 0;
     fence_mbar_init();
   }
   // weight tile (kidx, cc) as a B operand: K-major [n_tile x KC] (forward) or MN-major [KC x n_tile] (backward data)
@@ -161,103 +166,122 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
   const uint32_t tmem_base = ld_shared_volatile_u32(&ctl->tmem_slot);
 
   if (warp >= 4 && warp < 8) {
-    // ===================================== producers =====================================
-    const int pw = warp - 4, ptid = tid - 128;
-    const int sub = lane % LPR, rsel = lane / LPR;
-    uint32_t gi = 0;          // units (incl. END markers) produced so far; identical in all producer threads
-    int blk = 0;
-    int32_t idx[32], idx_n[32];
-    long long item = blockIdx.x;
-    int kb = 0;
-    bool have = item < n_items;
-    auto load_idx = [&](long long it_, int kb_, int32_t (&dst)[32]) {
-      const int64_t j = (it_ / n_ntiles) * kWsRows + pw * 32 + lane;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int kk = kb_ + k;
-        const int kp = flip ? kv - 1 - kk : kk;
-        dst[k] = (kk < kv && j < n_out) ? __ldg(pair + (int64_t)kp * pair_stride + j) : -1;
+    // ===================================== producers (thread = output row) =====================================
+    const int ptid = tid - 128;
+    // rulebook slice of one tile -> idx buffer `buf` (own row only; rows past n_out read a clamped address and are masked later)
+    auto fetch_idx = [&](long long item, int buf) {
+      int64_t j = (item / n_ntiles) * kWsRows + ptid;
+      if (j >= n_out) j = n_out - 1;
+      const uint32_t dst = smem_u32(idx_s + (size_t)buf * kv * kWsRows + ptid);
+      for (int k = 0; k < kv; ++k) {
+        const int kp = flip ? kv - 1 - k : k;
+        cp_async4(dst + k * (kWsRows * 4), pair + (int64_t)kp * pair_stride + j, true);
       }
     };
-    auto after_commit = [&]() {   // unit gi was just committed: signal unit gi - LAG, whose copies have landed
+    uint32_t gi = 0;                    // units (incl. END markers) committed so far
+    int st_i = 0, st_ph = 0;            // ring position of the next unit: stage and how often the ring wrapped (parity)
+    int arr_i = 0;                      // stage of the next unit to be signalled full
+    auto commit_unit = [&]() {          // close this unit's copy group; signal the unit LAG positions back, whose copies have landed
+      cp_async_commit();
       if (gi >= (uint32_t)LAG) {
-        cp_async_wait_dyn(LAG);
+        cp_async_wait<LAG>();
         fence_proxy_async();
-        mbar_arrive(&ctl->full[(gi - LAG) % S]);
+        mbar_arrive(&ctl->full[arr_i]);
+        if (++arr_i == S) arr_i = 0;
       }
       ++gi;
+      if (++st_i == S) { st_i = 0; st_ph ^= 1; }
     };
-    if (have) load_idx(item, 0, idx);
-    int units_in_item = 0;
-    while (have) {
-      uint32_t wmask = 0;
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (__any_sync(0xFFFFFFFFu, idx[k] >= 0)) wmask |= 1u << k;
-      const int slot = blk % 3;
-      if (lane == 0 && wmask) atomicOr(&ctl->mask_x[slot], wmask);
-      if (ptid == 0) ctl->mask_x[(blk + 1) % 3] = 0;
+    auto acquire_stage = [&]() {        // the MMAs that read this stage one ring turn ago have completed
+      if (gi >= (uint32_t)S) mbar_wait(&ctl->empty[st_i], st_ph ^ 1);
+    };
+    uint32_t tcount = 0;
+    long long item = blockIdx.x;
+    if (item < n_items) {
+      fetch_idx(item, 0);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
+    for (; item < n_items; item += gridDim.x, ++tcount) {
+      const int buf = tcount & 1, slot = tcount % 3;
+      const int32_t* my_idx = idx_s + (size_t)buf * kv * kWsRows + ptid;
+      const bool row_ok = (item / n_ntiles) * kWsRows + ptid < n_out;
+      // ---- which offsets have a partner anywhere in this tile ----
+      for (int k = 0; k < kv; ++k) {
+        const bool v = row_ok && my_idx[k * kWsRows] >= 0;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v);
+        if (lane == 0 && bal) atomicOr(&ctl->mask_x[slot][k >> 5], 1u << (k & 31));
+      }
+      if (ptid < 4) ctl->mask_x[(tcount + 1) % 3][ptid] = 0;
       named_bar_sync(1, 128);
-      uint32_t mask = ld_shared_volatile_u32(&ctl->mask_x[slot]);
-      long long nitem = item;
-      int nkb = kb + 32;
-      if (nkb >= kv) { nkb = 0; nitem = item + gridDim.x; }
-      const bool last_block = nkb == 0;
-      const bool nhave = nitem < n_items;
-      if (nhave) load_idx(nitem, nkb, idx_n);     // next block's rulebook slice is in flight while this block's rows are gathered
-      if (last_block && units_in_item == 0 && mask == 0) mask = 1;   // a tile always carries at least one (all-zero) unit
-      const int n0 = (int)(item % n_ntiles) * n_tile;
+      uint32_t mw[4];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        if (!((mask >> k) & 1u)) continue;
-        const int kidx = kb + k;
-        for (int cc = 0; cc < n_cc; ++cc) {
-          const int s = gi % S;
-          const uint32_t use = gi / S;
-          if (use > 0) mbar_wait(&ctl->empty[s], (use - 1) & 1);
-          uint8_t* a_s = ring + (size_t)s * stage_bytes;
-          const uint32_t a_dst = smem_u32(a_s) + sub * (kWsRows * 16) + (pw * 32 + rsel) * 16;
-#pragma unroll
-          for (int it = 0; it < LPR; ++it) {        // LPR iterations x RPI rows = this warp's 32 rows
-            const int32_t src = __shfl_sync(0xFFFFFFFFu, idx[k], it * RPI + rsel);
-            const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + cc * KC + sub * 8;
-            cp_async16(a_dst + it * RPI * 16, g, src >= 0);
-          }
-          if (!resident) load_w_tile(a_s + a_bytes, kidx, cc, n0, ptid, 128);
-          if (ptid == 0) ctl->meta[s] = (uint32_t)kidx | ((uint32_t)cc << 10) | (units_in_item == 0 ? kMetaFirst : 0u);
-          cp_async_commit();
-          after_commit();
-          ++units_in_item;
+      for (int w = 0; w < 4; ++w) mw[w] = ld_shared_volatile_u32(&ctl->mask_x[slot][w]);
+      int n_act = __popc(mw[0]) + __popc(mw[1]) + __popc(mw[2]) + __popc(mw[3]);
+      uint8_t* act = act_s + buf * kWsMaxKV;
+      {
+        const int wq = ptid >> 5;      // ptid < 128: word of this thread's offset
+        const uint32_t mine = wq == 0 ? mw[0] : (wq == 1 ? mw[1] : (wq == 2 ? mw[2] : mw[3]));
+        if (ptid < kv && ((mine >> (ptid & 31)) & 1u)) {
+          int pos = __popc(mine & ((1u << (ptid & 31)) - 1u));
+          if (wq > 0) pos += __popc(mw[0]);
+          if (wq > 1) pos += __popc(mw[1]);
+          if (wq > 2) pos += __popc(mw[2]);
+          act[pos] = (uint8_t)ptid;
         }
       }
-      if (last_block) {   // END marker: the MMA thread hands the accumulator to the epilogue warps
-        const int s = gi % S;
-        const uint32_t use = gi / S;
-        if (use > 0) mbar_wait(&ctl->empty[s], (use - 1) & 1);
-        if (ptid == 0) ctl->meta[s] = kMetaEnd;
-        cp_async_commit();
-        after_commit();
-        units_in_item = 0;
-      }
+      if (n_act == 0) { if (ptid == 0) act[0] = 0; n_act = 1; }   // a tile always carries at least one (all-zero) unit
+      named_bar_sync(1, 128);
+      // ---- next tile's rulebook slice rides in the copy group of this tile's first unit ----
+      const bool have_next = item + gridDim.x < n_items;
+      if (have_next) fetch_idx(item + gridDim.x, buf ^ 1);
+      const int n0 = (int)(item % n_ntiles) * n_tile;
+      const int n_units = n_act * n_cc;
+      bool first = true;
+      for (int a = 0; a < n_act; ++a) {
+        const int kidx = act[a];
+        const int32_t src = row_ok ? my_idx[kidx * kWsRows] : -1;
+        const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in;
+        for (int cc = 0; cc < n_cc; ++cc) {
+          acquire_stage();
+          uint8_t* a_s = ring + (size_t)st_i * stage_bytes;
+          const uint32_t a_dst = smem_u32(a_s) + ptid * 16;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) idx[k] = idx_n[k];
-      item = nitem; kb = nkb; have = nhave; ++blk;
+          for (int p = 0; p < LPR; ++p) cp_async16(a_dst + p * (kWsRows * 16), g + cc * KC + p * 8, src >= 0);
+          if (!resident) load_w_tile(a_s + a_bytes, kidx, cc, n0, ptid, 128);
+          if (ptid == 0) ctl->meta[st_i] = (uint32_t)kidx | ((uint32_t)cc << 10);
+          commit_unit();
+          first = false;
+        }
+      }
+      (void)first;
+      // END marker: the MMA thread hands the accumulator to the epilogue warps
+      acquire_stage();
+      if (ptid == 0) ctl->meta[st_i] = kMetaEnd;
+      commit_unit();
+      // the next tile's slice was committed n_units groups before the END group: make sure it has landed (own row only)
+      if (have_next && n_units < LAG) cp_async_wait_dyn(n_units);
     }
     // drain: the last LAG units
     cp_async_wait<0>();
     fence_proxy_async();
-    for (uint32_t u = gi >= (uint32_t)LAG ? gi - LAG : 0; u < gi; ++u) mbar_arrive(&ctl->full[u % S]);
+    for (uint32_t u = gi >= (uint32_t)LAG ? gi - LAG : 0; u < gi; ++u) {
+      mbar_arrive(&ctl->full[arr_i]);
+      if (++arr_i == S) arr_i = 0;
+    }
   } else if (warp == 8) {
     // ===================================== MMA issuer (whole warp waits, lane 0 issues) =====================================
     const uint32_t idesc = make_idesc(128, n_tile, UmmaFmt<T>::v, UmmaFmt<T>::v, 0, transpose_w ? 1 : 0);
-    uint32_t gi = 0, tcount = 0;
+    int st_i = 0, st_ph = 0;
+    uint32_t tcount = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1, ause = tcount >> 1;
       const uint32_t d_tmem = tmem_base + buf * n_tile;
       bool first = true;
       while (true) {
-        const int s = gi % S;
-        mbar_wait(&ctl->full[s], (gi / S) & 1);
+        const int s = st_i;
+        mbar_wait(&ctl->full[s], st_ph);
+        if (++st_i == S) { st_i = 0; st_ph ^= 1; }
         const uint32_t m = ld_shared_volatile_u32(&ctl->meta[s]);
         if (m & kMetaEnd) {
           if (lane == 0) {
@@ -265,7 +289,6 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
             mbar_arrive(&ctl->empty[s]);
           }
           __syncwarp();
-          ++gi;
           break;
         }
         if (first && ause > 0) mbar_wait(&ctl->acc_empty[buf], (ause - 1) & 1);   // epilogue drained this buffer
@@ -285,7 +308,6 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
         }
         __syncwarp();
         first = false;
-        ++gi;
       }
     }
   } else {
@@ -324,22 +346,23 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
   if (warp == 0) tmem_dealloc(tmem_base, cfg.tmem_cols);
 }
 
-template <typename T, int KC>
+template <typename T, int KC, int LAG>
 inline void launch_conv_ws_kc(const ConvWsCfg& c, const void* feat, const void* weight, const void* bias, const int32_t* pair,
                               int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, void* out,
                               cudaStream_t stream) {
-  cudaFuncSetAttribute(conv_ws_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
-  conv_ws_kernel<T, KC><<<c.grid, kWsThreads, c.smem_bytes, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride,
-                                                                      n_out, c_in, c_out, kv, transpose_w, flip, (T*)out, c);
+  cudaFuncSetAttribute(conv_ws_kernel<T, KC, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+  conv_ws_kernel<T, KC, LAG><<<c.grid, kWsThreads, c.smem_bytes, stream>>>((const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride,
+                                                                           n_out, c_in, c_out, kv, transpose_w, flip, (T*)out, c);
 }
 
 template <typename T>
 inline int launch_conv_ws_t(const void* feat, const void* weight, const void* bias, const int32_t* pair, int64_t pair_stride,
                             int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, void* out, cudaStream_t stream) {
   const ConvWsCfg c = conv_ws_cfg(n_out, c_in, c_out, kv);
-  if (c.kc == 64) launch_conv_ws_kc<T, 64>(c, feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream);
-  else if (c.kc == 32) launch_conv_ws_kc<T, 32>(c, feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream);
-  else launch_conv_ws_kc<T, 16>(c, feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream);
+#define B2PC_WS_GO(KC_, LAG_) launch_conv_ws_kc<T, KC_, LAG_>(c, feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream)
+  if (c.lag == 6) { if (c.kc == 64) B2PC_WS_GO(64, 6); else if (c.kc == 32) B2PC_WS_GO(32, 6); else B2PC_WS_GO(16, 6); }
+  else { if (c.kc == 64) B2PC_WS_GO(64, 2); else if (c.kc == 32) B2PC_WS_GO(32, 2); else B2PC_WS_GO(16, 2); }
+#undef B2PC_WS_GO
   count_launches(1);
   B2PC_CHECK_LAUNCH("spconv_gather_gemm(tcgen05, warp-specialised)");
   return B2PC_OK;
@@ -368,14 +391,15 @@ constexpr int kWg2MaxStages = 12;
 constexpr int kWg2NB = 3;             // dout tile buffers
 
 struct WgradWsCfg {
-  int mc, n_chunks_c, spm, m_tiles, n_tile, n_ntiles, tpg, n_mgroups, n_splits, stages, lag, tmem_cols, a_bytes, b_bytes, smem_bytes;
+  int mc, n_chunks_c, spm, m_tiles, n_tile, n_ntiles, tpg, n_mgroups, n_splits, stages, lag, tmem_cols, a_bytes, b_bytes, idx_bytes, kspan,
+      smem_bytes;
   long long n_row_chunks;
 };
 
 inline bool wgrad_ws_supported(int dtype, int c_in, int c_out, int kv) {
   if (dtype != B2PC_F16 && dtype != B2PC_BF16) return false;
   if (c_in % 16 != 0 || c_out % 16 != 0) return false;
-  if (kv > 343) return false;
+  if (kv > kWsMaxKV) return false;
   return true;
 }
 
@@ -399,20 +423,22 @@ inline WgradWsCfg wgrad_ws_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   while (c.tmem_cols < c.tpg * c.n_tile) c.tmem_cols <<= 1;
   c.n_row_chunks = ceil_div(n_out > 0 ? n_out : 1, kWg2Rows);
   const int groups = c.n_mgroups * c.n_ntiles;
-  const int per_sm = 1;   // one persistent CTA per SM: the deep gather ring, not a second CTA, hides the latency
-  long long sp = ceil_div((long long)per_sm * kNumSMs, groups);
+  long long sp = ceil_div((long long)kNumSMs, groups);   // one persistent CTA per SM: the deep gather ring hides the latency
   if (sp > c.n_row_chunks) sp = c.n_row_chunks;
   if (sp < 1) sp = 1;
   c.n_splits = (int)sp;
   c.a_bytes = 128 * kWg2Rows * 2;
   c.b_bytes = kWg2Rows * c.n_tile * 2;
-  const int budget = (per_sm == 2 ? 100 : 200) * 1024;
-  int st = (budget - kWsCtrlBytes - kWg2NB * c.b_bytes) / c.a_bytes;
+  // kernel offsets one CTA touches: the slots of its M-tile group span at most this many offsets
+  c.kspan = (c.tpg * c.spm + c.n_chunks_c - 1) / c.n_chunks_c + 1;
+  if (c.kspan > kv) c.kspan = kv;
+  c.idx_bytes = 2 * c.kspan * kWg2Rows * 4;
+  int st = (kWsSmemBudget - kWsCtrlBytes - kWg2NB * c.b_bytes - c.idx_bytes) / c.a_bytes;
   if (st > kWg2MaxStages) st = kWg2MaxStages;
   if (st < 3) st = 3;
   c.stages = st;
-  c.lag = st - 2 > 12 ? 12 : st - 2;
-  c.smem_bytes = kWsCtrlBytes + kWg2NB * c.b_bytes + c.stages * c.a_bytes;
+  c.lag = st >= 8 ? 6 : 2;
+  c.smem_bytes = kWsCtrlBytes + c.idx_bytes + kWg2NB * c.b_bytes + c.stages * c.a_bytes;
   return c;
 }
 
@@ -431,21 +457,24 @@ struct WgCtrl {
 };
 static_assert(sizeof(WgCtrl) <= kWsCtrlBytes, "control block too large");
 
-template <typename T, int MC>
+// Producer mapping: thread (r = tid & 63, h = tid >> 6) owns row r of the 64-row chunk and, of every slot of a unit, the h-th half
+// of its MC channels (MC/16 contiguous 16-byte pieces from one base pointer).  The rulebook slice of the NEXT chunk (only the
+// kernel offsets this CTA's M-tile group touches) is fetched by 4-byte cp.async into a second buffer while the current chunk streams.
+template <typename T, int MC, int LAG>
 __global__ void __launch_bounds__(kWg2Threads)
 wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const int32_t* __restrict__ pair, int64_t pair_stride,
                 int64_t n_out, int c_in, int c_out, int kv, float* __restrict__ dst_base, WgradWsCfg cfg) {
   using namespace umma;
   extern __shared__ __align__(128) uint8_t smem[];
   WgCtrl* ctl = reinterpret_cast<WgCtrl*>(smem);
-  uint8_t* b_ring = smem + kWsCtrlBytes;
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem + kWsCtrlBytes);       // [2][kspan][64]
+  uint8_t* b_ring = smem + kWsCtrlBytes + cfg.idx_bytes;
   uint8_t* a_ring = b_ring + kWg2NB * cfg.b_bytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int SPM = 128 / MC;     // slots per M tile
-  constexpr int LPR = MC / 8;       // lanes per gathered row (2, 4, 8, 16)
-  constexpr int RPI = 32 / LPR;     // rows per warp instruction
-  constexpr int NIT = 16 / RPI > 0 ? 16 / RPI : 1;   // iterations to cover this warp's 16 rows of a slot
-  const int S = cfg.stages, LAG = cfg.lag, n_tile = cfg.n_tile;
+  constexpr int LPR = MC / 8;       // 16-byte pieces per gathered row of one slot
+  constexpr int PPT = LPR / 2;      // pieces per producer thread per slot (two threads share a row)
+  const int S = cfg.stages, n_tile = cfg.n_tile;
   const int split = blockIdx.x, n_splits = gridDim.x;
   const int mgroup = blockIdx.y % cfg.n_mgroups, nt_i = blockIdx.y / cfg.n_mgroups;
   const int mt0 = mgroup * cfg.tpg;
@@ -454,7 +483,9 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
   const int n_cc = cfg.n_chunks_c;
   const int slots_total = kv * n_cc;
   const long long n_rc = cfg.n_row_chunks;
-  const int a_bytes = cfg.a_bytes, b_bytes = cfg.b_bytes;
+  const int a_bytes = cfg.a_bytes, b_bytes = cfg.b_bytes, kspan = cfg.kspan;
+  const int k_lo = (mt0 * SPM) / n_cc;                   // first kernel offset this CTA touches
+  const int k_cnt = min(kspan, kv - k_lo);
 
   if (warp == 0) { tmem_alloc(&ctl->tmem_slot, cfg.tmem_cols); tmem_relinquish(); }
   if (tid == 32) {
@@ -470,76 +501,76 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
 
   if (warp < 4) {
     // ===================================== producers =====================================
-    const int sub = lane % LPR, rsel = lane / LPR;
+    const int r = tid & 63, h = tid >> 6;
+    auto fetch_idx = [&](long long rc, int buf) {   // thread (r, h) fetches row r of the offsets k_lo + h, k_lo + h + 2, ...
+      int64_t j = rc * kWg2Rows + r;
+      if (j >= n_out) j = n_out - 1;
+      const uint32_t dst = smem_u32(idx_s + (size_t)buf * kspan * kWg2Rows + r);
+      for (int kk = h; kk < k_cnt; kk += 2) cp_async4(dst + kk * (kWg2Rows * 4), pair + (int64_t)(k_lo + kk) * pair_stride + j, true);
+    };
     uint32_t gi = 0;
-    auto after_commit = [&]() {
+    int st_i = 0, st_ph = 0, arr_i = 0;
+    auto commit_unit = [&]() {
+      cp_async_commit();
       if (gi >= (uint32_t)LAG) {
-        cp_async_wait_dyn(LAG);
+        cp_async_wait<LAG>();
         fence_proxy_async();
-        mbar_arrive(&ctl->full[(gi - LAG) % S]);
+        mbar_arrive(&ctl->full[arr_i]);
+        if (++arr_i == S) arr_i = 0;
       }
       ++gi;
+      if (++st_i == S) { st_i = 0; st_ph ^= 1; }
     };
-    // rulebook entries of one unit: slot sl of M tile mt, this warp's 16 rows (lanes 0-15; lanes 16-31 mirror them)
-    auto load_idx = [&](long long rc, int mt, int32_t (&dst)[SPM]) {
-      const int64_t j = rc * kWg2Rows + warp * 16 + (lane & 15);
-#pragma unroll
-      for (int sl = 0; sl < SPM; ++sl) {
-        const int slot = (mt0 + mt) * SPM + sl;
-        const int k = slot / n_cc;
-        dst[sl] = (slot < slots_total && j < n_out) ? __ldg(pair + (int64_t)k * pair_stride + j) : -1;
-      }
-    };
-    int32_t cur[SPM], nxt[SPM];
-    long long rc = split;
-    int mt = 0;
-    bool have = rc < n_rc;
-    if (have) load_idx(rc, 0, cur);
     uint32_t chunk_local = 0;
-    while (have) {
-      long long nrc = rc;
-      int nmt = mt + 1;
-      if (nmt >= n_mt) { nmt = 0; nrc = rc + n_splits; }
-      const bool nhave = nrc < n_rc;
-      if (nhave) load_idx(nrc, nmt, nxt);
-      const int s = gi % S;
-      const uint32_t use = gi / S;
-      if (use > 0) mbar_wait(&ctl->empty[s], (use - 1) & 1);
-      if (mt == 0) {   // dout tile of this chunk (operand B, MN-major planes): rides in the first unit's copy group
-        const int b = chunk_local % kWg2NB;
-        if (chunk_local >= (uint32_t)kWg2NB) mbar_wait(&ctl->bempty[b], ((chunk_local / kWg2NB) - 1) & 1);
-        const int ppr = n_tile / 8;
-        const uint32_t b_dst = smem_u32(b_ring + (size_t)b * b_bytes);
-        for (int q = tid; q < kWg2Rows * ppr; q += 128) {
-          const int r = q / ppr, p = q % ppr;
-          const int64_t j = rc * kWg2Rows + r;
-          cp_async16(b_dst + p * (kWg2Rows * 16) + r * 16, dout + (j < n_out ? j : 0) * c_out + n0 + p * 8, j < n_out);
-        }
-      }
-      const uint32_t a_dst = smem_u32(a_ring + (size_t)s * a_bytes) + (warp * 16 + rsel) * 16;
-#pragma unroll
-      for (int sl = 0; sl < SPM; ++sl) {
-        const int slot = (mt0 + mt) * SPM + sl;
-        const int cchunk = slot % n_cc;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-          const int r = it * RPI + rsel;                 // row inside this warp's 16
-          const int32_t src = __shfl_sync(0xFFFFFFFFu, cur[sl], r & 15);
-          const bool ok = src >= 0 && r < 16;
-          const T* g = feat + (int64_t)(ok ? src : 0) * c_in + cchunk * MC + sub * 8;
-          if (r < 16) cp_async16(a_dst + (sl * LPR + sub) * (kWg2Rows * 16) + it * RPI * 16, g, ok);
-        }
-      }
+    long long rc = split;
+    if (rc < n_rc) {
+      fetch_idx(rc, 0);
       cp_async_commit();
-      after_commit();
+      cp_async_wait<0>();
+    }
+    for (; rc < n_rc; rc += n_splits, ++chunk_local) {
+      const int buf = chunk_local & 1;
+      named_bar_sync(1, 128);                      // the other half-row thread's index copies are visible; previous chunk fully issued
+      const bool have_next = rc + n_splits < n_rc;
+      if (have_next) fetch_idx(rc + n_splits, buf ^ 1);
+      const bool row_ok = rc * kWg2Rows + r < n_out;
+      const int32_t* my_idx = idx_s + (size_t)buf * kspan * kWg2Rows + r;
+      for (int mt = 0; mt < n_mt; ++mt) {
+        if (gi >= (uint32_t)S) mbar_wait(&ctl->empty[st_i], st_ph ^ 1);
+        if (mt == 0) {   // dout tile of this chunk (operand B, MN-major planes): rides in the first unit's copy group
+          const int b = chunk_local % kWg2NB;
+          if (chunk_local >= (uint32_t)kWg2NB) mbar_wait(&ctl->bempty[b], ((chunk_local / kWg2NB) - 1) & 1);
+          const int ppr = n_tile / 8;
+          const uint32_t b_dst = smem_u32(b_ring + (size_t)b * b_bytes);
+          for (int q = tid; q < kWg2Rows * ppr; q += 128) {
+            const int rr = q / ppr, p = q % ppr;
+            const int64_t j = rc * kWg2Rows + rr;
+            cp_async16(b_dst + p * (kWg2Rows * 16) + rr * 16, dout + (j < n_out ? j : 0) * c_out + n0 + p * 8, j < n_out);
+          }
+        }
+        const uint32_t a_dst = smem_u32(a_ring + (size_t)st_i * a_bytes) + r * 16;
+        int slot = (mt0 + mt) * SPM;
+        int k = slot / n_cc, cchunk = slot % n_cc;
 #pragma unroll
-      for (int sl = 0; sl < SPM; ++sl) cur[sl] = nxt[sl];
-      if (nmt == 0) ++chunk_local;
-      rc = nrc; mt = nmt; have = nhave;
+        for (int sl = 0; sl < SPM; ++sl) {
+          const int32_t src = (slot < slots_total && row_ok) ? my_idx[(k - k_lo) * kWg2Rows] : -1;
+          const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + cchunk * MC + h * (PPT * 8);
+#pragma unroll
+          for (int q = 0; q < PPT; ++q) cp_async16(a_dst + (sl * LPR + h * PPT + q) * (kWg2Rows * 16), g + q * 8, src >= 0);
+          ++slot;
+          if (++cchunk == n_cc) { cchunk = 0; ++k; }
+        }
+        commit_unit();
+      }
+      // the next chunk's slice was committed n_mt - 1 groups before the last unit: make sure this thread's part has landed
+      if (have_next && n_mt - 1 < LAG) cp_async_wait_dyn(n_mt - 1);
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (uint32_t u = gi >= (uint32_t)LAG ? gi - LAG : 0; u < gi; ++u) mbar_arrive(&ctl->full[u % S]);
+    for (uint32_t u = gi >= (uint32_t)LAG ? gi - LAG : 0; u < gi; ++u) {
+      mbar_arrive(&ctl->full[arr_i]);
+      if (++arr_i == S) arr_i = 0;
+    }
     // ===================================== epilogue (same warps; TMEM lane quarter = warp) =====================================
     mbar_wait(&ctl->done, 0);
     tc_fence_after();
@@ -553,25 +584,27 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
       const int k = slot / n_cc, ci = (slot % n_cc) * MC + ch;
       const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + t * n_tile;
       for (int cb = 0; cb < n_tile; cb += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + cb, r);
+        uint32_t rg[16];
+        tmem_ld16(t_addr + cb, rg);
         tmem_ld_wait();
         if (ok) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) dst_split[(int64_t)(n0 + cb + e) * kvc + (int64_t)k * c_in + ci] = __uint_as_float(r[e]);
+          for (int e = 0; e < 16; ++e) dst_split[(int64_t)(n0 + cb + e) * kvc + (int64_t)k * c_in + ci] = __uint_as_float(rg[e]);
         }
       }
     }
   } else {
     // ===================================== MMA issuer (whole warp waits, lane 0 issues) =====================================
     const uint32_t idesc = make_idesc(128, n_tile, UmmaFmt<T>::v, UmmaFmt<T>::v, 1, 1);
-    uint32_t gi = 0, chunk_local = 0;
+    int st_i = 0, st_ph = 0;
+    uint32_t chunk_local = 0;
     for (long long rc = split; rc < n_rc; rc += n_splits, ++chunk_local) {
       const int b = chunk_local % kWg2NB;
       const uint32_t b_addr = smem_u32(b_ring + (size_t)b * b_bytes);
-      for (int t = 0; t < n_mt; ++t, ++gi) {
-        const int s = gi % S;
-        mbar_wait(&ctl->full[s], (gi / S) & 1);
+      for (int t = 0; t < n_mt; ++t) {
+        const int s = st_i;
+        mbar_wait(&ctl->full[s], st_ph);
+        if (++st_i == S) { st_i = 0; st_ph ^= 1; }
         if (lane == 0) {
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_ring + (size_t)s * a_bytes);
@@ -593,13 +626,13 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
   if (warp == 0) tmem_dealloc(tmem_base, cfg.tmem_cols);
 }
 
-template <typename T, int MC>
+template <typename T, int MC, int LAG>
 inline void launch_wgrad_ws_mc(const WgradWsCfg& c, const void* feat, const void* dout, const int32_t* pair, int64_t pair_stride,
                                int64_t n_out, int c_in, int c_out, int kv, float* dst, cudaStream_t stream) {
-  cudaFuncSetAttribute(wgrad_ws_kernel<T, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
+  cudaFuncSetAttribute(wgrad_ws_kernel<T, MC, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
   dim3 grid(c.n_splits, c.n_mgroups * c.n_ntiles);
-  wgrad_ws_kernel<T, MC><<<grid, kWg2Threads, c.smem_bytes, stream>>>((const T*)feat, (const T*)dout, pair, pair_stride, n_out, c_in, c_out,
-                                                                     kv, dst, c);
+  wgrad_ws_kernel<T, MC, LAG><<<grid, kWg2Threads, c.smem_bytes, stream>>>((const T*)feat, (const T*)dout, pair, pair_stride, n_out, c_in,
+                                                                          c_out, kv, dst, c);
 }
 
 template <typename T>
@@ -607,12 +640,13 @@ inline int launch_wgrad_ws_t(const void* feat, const void* dout, const int32_t* 
                              int c_out, int kv, float* dweight, void* ws, cudaStream_t stream) {
   const WgradWsCfg c = wgrad_ws_cfg(n_out, c_in, c_out, kv);
   float* dst = c.n_splits > 1 ? (float*)ws : dweight;
-  switch (c.mc) {
-    case 128: launch_wgrad_ws_mc<T, 128>(c, feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dst, stream); break;
-    case 64: launch_wgrad_ws_mc<T, 64>(c, feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dst, stream); break;
-    case 32: launch_wgrad_ws_mc<T, 32>(c, feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dst, stream); break;
-    default: launch_wgrad_ws_mc<T, 16>(c, feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dst, stream); break;
+#define B2PC_WG_GO(MC_, LAG_) launch_wgrad_ws_mc<T, MC_, LAG_>(c, feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dst, stream)
+  if (c.lag == 6) {
+    switch (c.mc) { case 128: B2PC_WG_GO(128, 6); break; case 64: B2PC_WG_GO(64, 6); break; case 32: B2PC_WG_GO(32, 6); break; default: B2PC_WG_GO(16, 6); }
+  } else {
+    switch (c.mc) { case 128: B2PC_WG_GO(128, 2); break; case 64: B2PC_WG_GO(64, 2); break; case 32: B2PC_WG_GO(32, 2); break; default: B2PC_WG_GO(16, 2); }
   }
+#undef B2PC_WG_GO
   count_launches(1);
   if (c.n_splits > 1) {
     const int64_t elems = (int64_t)c_out * kv * c_in;

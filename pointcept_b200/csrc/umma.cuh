@@ -16,10 +16,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// A wait that never completes would hang the GPU; after ~2^26 failed polls (seconds -- no legitimate wait in this library is
+// longer than a kernel's own runtime of well under a second) the kernel traps instead, turning a pipeline deadlock into a CUDA error.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+  uint32_t polls = 0;
   do {
+    if (++polls == (1u << 26)) __trap();
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"

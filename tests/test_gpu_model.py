@@ -87,12 +87,23 @@ def test_ptv3_tiny_backward_all_parameter_gradients_vs_cpu_oracle(golden_dir):
                            bn_training=True, attn_dtype=torch.bfloat16)
     ref.backward(dout)
     assert rel_l2(out.detach(), ref.detach()) < 5e-3
-    worst = {}
+    # Parameters whose gradient is zero in exact arithmetic (a bias in front of BatchNorm, the key bias of the attention: softmax
+    # is shift invariant) hold pure rounding noise on both sides; they are checked for smallness instead of relative error.
+    gmax = max(float(v.grad.norm()) for k, v in sdr.items() if v.grad is not None)
+    worst, noise = {}, {}
     for k, p in model.named_parameters():
         assert p.grad is not None, k
-        worst[k] = rel_l2(p.grad, sdr[k].grad)
+        rn = float(sdr[k].grad.norm())
+        if rn < 1e-5 * gmax:
+            noise[k] = float(p.grad.norm()) / gmax
+        else:
+            worst[k] = rel_l2(p.grad, sdr[k].grad)
+    print("largest relative gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    print("parameters with (numerically) zero reference gradient:", len(noise), "max |g|/gmax", max(noise.values()) if noise else 0.0)
+    assert len(worst) > 100
     bad = {k: v for k, v in worst.items() if v >= 1e-2}
     assert not bad, bad
+    assert all(v < 1e-4 for v in noise.values()), noise
 
 
 @pytest.mark.parametrize("amp", [torch.bfloat16, torch.float16])
@@ -120,13 +131,16 @@ def test_ptv3_tiny_autocast_runs_tensor_core_convs_and_matches_oracle(golden_dir
     finally:
         ops.set_impl(old)
     assert scaler.get_scale() >= 1024.0 or amp != torch.float16          # no inf/nan was found: the step was not skipped
-    # half-precision rounding at every Linear / conv boundary vs the reference model's fp32 run: 3e-2 on the output after 10 blocks
-    assert rel_l2(out.detach().float(), torch.from_numpy(g["out"])) < 3e-2
+    # half-precision rounding at every Linear / conv boundary (8 / 11 mantissa bits) vs the reference model's fp32 run, 10 blocks
+    # deep: 5e-2 on the output, 2e-1 on weight gradients for bf16; fp16 (the stock AMP dtype) 1e-2 / 5e-2
+    e_out = rel_l2(out.detach().float(), torch.from_numpy(g["out"]))
     grads = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("grad::")}
     params = dict(model.named_parameters())
-    for k, ref in grads.items():
-        assert torch.isfinite(params[k].grad).all()
-        assert rel_l2(params[k].grad, ref) < 8e-2, k
+    e_g = {k: rel_l2(params[k].grad, ref) for k, ref in grads.items()}
+    print("autocast", amp, "out", e_out, "grads", e_g)
+    assert all(torch.isfinite(params[k].grad).all() for k in grads)
+    assert e_out < (5e-2 if amp == torch.bfloat16 else 1e-2)
+    assert max(e_g.values()) < (2e-1 if amp == torch.bfloat16 else 5e-2), e_g
 
 
 def test_spatial_reorder_is_permutation_equivalent(golden_dir):

@@ -91,8 +91,9 @@ inline ConvWsCfg conv_ws_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   if (st < 3) st = 3;
   c.stages = st;
   c.lag = st >= 8 ? 6 : 2;
-  c.tmem_cols = 32;
-  while (c.tmem_cols < 2 * c.n_tile) c.tmem_cols <<= 1;
+  int ncol = 32;                        // accumulator buffers sit on power-of-two column strides (N = 96 tiles at column 96 fault)
+  while (ncol < c.n_tile) ncol <<= 1;
+  c.tmem_cols = 2 * ncol;
   c.smem_bytes = kWsCtrlBytes + c.idx_bytes + c.res_bytes + c.stages * c.stage_bytes;
   c.grid = (int)(c.n_items < kNumSMs ? c.n_items : kNumSMs);
   return c;
@@ -276,7 +277,7 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
     uint32_t tcount = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1, ause = tcount >> 1;
-      const uint32_t d_tmem = tmem_base + buf * n_tile;
+      const uint32_t d_tmem = tmem_base + buf * (cfg.tmem_cols >> 1);
       bool first = true;
       while (true) {
         const int s = st_i;
@@ -319,7 +320,7 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
       tc_fence_after();
       const int64_t j = (item / n_ntiles) * kWsRows + warp * 32 + lane;
       const int n0 = (int)(item % n_ntiles) * n_tile;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * n_tile;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * (cfg.tmem_cols >> 1);
       for (int cb = 0; cb < n_tile; cb += 16) {
         uint32_t r[16];
         tmem_ld16(t_addr + cb, r);
@@ -391,8 +392,8 @@ constexpr int kWg2MaxStages = 12;
 constexpr int kWg2NB = 3;             // dout tile buffers
 
 struct WgradWsCfg {
-  int mc, n_chunks_c, spm, m_tiles, n_tile, n_ntiles, tpg, n_mgroups, n_splits, stages, lag, tmem_cols, a_bytes, b_bytes, idx_bytes, kspan,
-      smem_bytes;
+  int mc, n_chunks_c, spm, m_tiles, n_tile, n_ntiles, ncol, tpg, n_mgroups, n_splits, stages, lag, tmem_cols, a_bytes, b_bytes, idx_bytes,
+      kspan, smem_bytes;
   long long n_row_chunks;
 };
 
@@ -416,11 +417,13 @@ inline WgradWsCfg wgrad_ws_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   for (int nt = c_out <= 256 ? c_out : 256; nt >= 16; nt -= 16)
     if (c_out % nt == 0) { c.n_tile = nt; break; }
   c.n_ntiles = c_out / c.n_tile;
-  c.tpg = 512 / c.n_tile;
+  c.ncol = 32;                          // accumulator slices sit on power-of-two column strides
+  while (c.ncol < c.n_tile) c.ncol <<= 1;
+  c.tpg = 512 / c.ncol;
   if (c.tpg > c.m_tiles) c.tpg = c.m_tiles;
   c.n_mgroups = (c.m_tiles + c.tpg - 1) / c.tpg;
   c.tmem_cols = 32;
-  while (c.tmem_cols < c.tpg * c.n_tile) c.tmem_cols <<= 1;
+  while (c.tmem_cols < c.tpg * c.ncol) c.tmem_cols <<= 1;
   c.n_row_chunks = ceil_div(n_out > 0 ? n_out : 1, kWg2Rows);
   const int groups = c.n_mgroups * c.n_ntiles;
   long long sp = ceil_div((long long)kNumSMs, groups);   // one persistent CTA per SM: the deep gather ring hides the latency
@@ -582,7 +585,7 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
       const int slot = (mt0 + t) * SPM + sl;
       const bool ok = slot < slots_total;
       const int k = slot / n_cc, ci = (slot % n_cc) * MC + ch;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + t * n_tile;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + t * cfg.ncol;
       for (int cb = 0; cb < n_tile; cb += 16) {
         uint32_t rg[16];
         tmem_ld16(t_addr + cb, rg);
@@ -610,7 +613,7 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
           const uint32_t a_addr = smem_u32(a_ring + (size_t)s * a_bytes);
 #pragma unroll
           for (int ks = 0; ks < kWg2Rows / 16; ++ks)
-            mma_ss(tmem_base + t * n_tile, make_smem_desc(a_addr + ks * 256, 128, kWg2Rows * 16),
+            mma_ss(tmem_base + t * cfg.ncol, make_smem_desc(a_addr + ks * 256, 128, kWg2Rows * 16),
                    make_smem_desc(b_addr + ks * 256, 128, kWg2Rows * 16), idesc, (chunk_local > 0 || ks > 0) ? 1u : 0u);
           mma_commit(&ctl->empty[s]);
           if (t == n_mt - 1) mma_commit(&ctl->bempty[b]);

@@ -424,7 +424,9 @@ struct FusedResidualFn : public torch::autograd::Function<FusedResidualFn> {
     if (gaf.defined()) { dga = at::empty({c}, r.options()); dba = at::empty({c}, r.options()); }
     if (gbf.defined()) { dgb = at::empty({c}, r.options()); dbb = at::empty({c}, r.options()); }
     const int64_t xbd = ctx->saved_data["xb_dtype"].toInt();
-    Tensor dxb = (xbd >= 0 && ctx->needs_input_grad(11)) ? at::empty({c}, r.options()) : Tensor();
+    // (needs_input_grad() indexes the VARIABLE inputs only -- absent optional tensors shift it -- so the request is keyed on the
+    // argument having been passed; the bias is a leaf parameter whenever it is)
+    Tensor dxb = xbd >= 0 ? at::empty({c}, r.options()) : Tensor();
     Tensor ws = workspace(b2pc_fused_residual_bwd_workspace_bytes(n, (int)c), x);
     check(b2pc_fused_residual_bwd(fptr(dr_out), optr(dr16), optr(dy), dt(x), r.data_ptr<float>(), x.data_ptr(), fptr(uf),
                                   (float)ctx->saved_data["keep"].toDouble(), fptr(gaf), fptr(gbf), fptr(sa), fptr(sb), n, (int)c,

@@ -53,13 +53,24 @@ def main():
         t0 = time.time()
         for impl in (1, 2):
             ops.set_impl(impl)
-            fwd = ops._gather_gemm(feat, w, None, pair, n, cin, cout, kv, False, False)
-            bwd = ops._gather_gemm(dout, w, None, pair, n, cout, cin, kv, True, True)
-            f2 = feat.clone().requires_grad_(True)
-            w2 = w.float().requires_grad_(True)
-            ops.sparse_conv(f2, w2, None, pair, pair, True).backward(dout)
-            torch.cuda.synchronize()
-            res[impl] = (fwd.float(), bwd.float(), w2.grad.clone())
+            stage = "fwd"
+            try:
+                fwd = ops._gather_gemm(feat, w, None, pair, n, cin, cout, kv, False, False)
+                torch.cuda.synchronize()
+                stage = "bwd_data"
+                bwd = ops._gather_gemm(dout, w, None, pair, n, cout, cin, kv, True, True)
+                torch.cuda.synchronize()
+                stage = "bwd_weight"
+                dw = torch.empty((cout, kv, cin), dtype=torch.float32, device=DEV)
+                L = ops._lib.lib()
+                ws = ops._ws(L.b2pc_spconv_bwd_weight_workspace_bytes(n, cin, cout, kv), DEV)
+                ops._lib.check(L.b2pc_spconv_bwd_weight(ops._p(feat), ops._p(dout), ops._p(pair), pair.shape[1], n, n, cin, cout, kv, 2,
+                                                        ops._p(dw), ops._p(ws), ws.numel(), impl, ops._stream()), "bwd_weight")
+                torch.cuda.synchronize()
+            except Exception as e:
+                print(f"N={n} {cin}->{cout} kv={kv} impl={impl}: FAILED in {stage}: {str(e)[:120]}", flush=True)
+                sys.exit(2)
+            res[impl] = (fwd.float(), bwd.float(), dw)
         ops.set_impl(0)
         e = [rel(a, b) for a, b in zip(res[2], res[1])]
         ok = all(v < 3e-3 for v in e)

@@ -247,6 +247,11 @@ int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks
 /* Exact (erf) GELU over n_elems values (n_elems % 4 == 0), forward and backward (nn.GELU, point_transformer_v3m1_base.py:233). */
 int b2pc_gelu_fwd(const void* x, int dtype, int64_t n_elems, void* y, b2pc_stream_t stream);
 int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, void* dx, b2pc_stream_t stream);
+/* GELU backward over [n, c] that also returns colsum[c] = sum_rows dx (fp32): the bias gradient of the Linear feeding the GELU
+ * (MLP.fc1, point_transformer_v3m1_base.py:238) without a separate pass over the largest activation of the block. */
+size_t b2pc_gelu_bwd_colsum_workspace_bytes(int64_t n, int c);
+int b2pc_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int64_t n, int c, void* dx, float* colsum, void* workspace,
+                         size_t workspace_bytes, b2pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Built-in per-entry-point timing (bench.py's roofline leg; binding independent because it lives below the C ABI).

@@ -429,6 +429,15 @@ int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, voi
   return B2PC_OK;
 }
 
+size_t b2pc_gelu_bwd_colsum_workspace_bytes(int64_t n, int c) { return gelu_bwd_colsum_workspace_bytes(n, c); }
+
+int b2pc_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int64_t n, int c, void* dx, float* colsum, void* workspace,
+                         size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
+  B2PC_CHECK_ARG(dy && x && dx && colsum && workspace, "gelu_bwd_colsum: null pointer");
+  return launch_gelu_bwd_colsum(dy, x, dtype, n, c, dx, colsum, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 void b2pc_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (on) {

@@ -277,24 +277,34 @@ fused_param_reduce_kernel(const float* __restrict__ part, int blocks, int c, flo
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane;
   float* outs[5] = {o0, o1, o2, o3, o4};
-  for (int v = 0; v < 5; ++v) {
-    if (!outs[v]) continue;
-    float acc = 0.f;
-    for (int b = grp; b < blocks; b += 8) acc += part[((int64_t)b * 5 + v) * c + ch];
-    __syncthreads();
-    sm[grp][lane] = acc;
-    __syncthreads();
-    if (grp == 0) {
-      float t = 0.f;
+  const int v = blockIdx.y;                 // one parameter vector per grid row
+  if (!outs[v]) return;
+  float acc0 = 0.f, acc1 = 0.f;             // two independent chains (fixed order: deterministic)
+  int b = grp;
+  for (; b + 8 < blocks; b += 16) {
+    acc0 += part[((int64_t)b * 5 + v) * c + ch];
+    acc1 += part[((int64_t)(b + 8) * 5 + v) * c + ch];
+  }
+  if (b < blocks) acc0 += part[((int64_t)b * 5 + v) * c + ch];
+  sm[grp][lane] = acc0 + acc1;
+  __syncthreads();
+  if (grp == 0) {
+    float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += sm[w][lane];
-      outs[v][ch] = t;
-    }
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    outs[v][ch] = t;
   }
 }
 
 inline bool fused_channels_ok(int c) { return c == 32 || c == 64 || c == 128 || c == 256 || c == 512; }
-inline size_t fused_residual_bwd_workspace_bytes(int64_t n, int c) { return (size_t)ln_blocks(n) * 5 * c * sizeof(float) + 256; }
+// HBM-bound streaming kernels: enough resident warps to keep tens of KB in flight per SM (ncu: 2 blocks per SM reached 27 % of
+// the copy bandwidth); the backward is limited to 4 blocks per SM by its 32 KB reduction scratch
+inline int fused_blocks(int64_t n, int per_sm) {
+  int64_t b = ceil_div(n, kLnThreads / 32 * 4);
+  if (b > kNumSMs * per_sm) b = kNumSMs * per_sm;
+  return (int)(b < 1 ? 1 : b);
+}
+inline size_t fused_residual_bwd_workspace_bytes(int64_t n, int c) { return (size_t)fused_blocks(n, 4) * 5 * c * sizeof(float) + 256; }
 
 #define B2PC_FR_DISPATCH(DT, VV, KERNEL, ...)                                                          \
   do {                                                                                                 \
@@ -311,7 +321,7 @@ inline int launch_fused_residual_fwd(const FusedResArgs& a, int dtype, cudaStrea
   B2PC_CHECK_ARG((!a.ga || a.stat_a) && (!a.gb || a.stat_b), "fused_residual_fwd: statistics buffer missing");
   if (a.n == 0) return B2PC_OK;
   const int vv = a.c <= 128 ? 1 : (a.c == 256 ? 2 : 4);
-  const int blocks = ln_blocks(a.n);
+  const int blocks = fused_blocks(a.n, 8);
   B2PC_FR_DISPATCH(dtype, vv, fused_residual_fwd_kernel, <<<blocks, kLnThreads, 0, stream>>>(a));
   count_launches(1);
   B2PC_CHECK_LAUNCH("fused_residual_fwd");
@@ -341,12 +351,12 @@ inline int launch_fused_residual_bwd(const FusedResBwdArgs& a0, int dtype, float
   const int vv = a.c <= 128 ? 1 : (a.c == 256 ? 2 : 4);
   const int rpw = 32 / (a.c / (4 * vv));
   const size_t smem = (size_t)2 * (kLnThreads / 32) * rpw * a.c * sizeof(float);   // <= 32 KB
-  const int blocks = ln_blocks(a.n);
+  const int blocks = fused_blocks(a.n, 4);
   B2PC_FR_DISPATCH(dtype, vv, fused_residual_bwd_kernel, <<<blocks, kLnThreads, smem, stream>>>(a));
   count_launches(1);
   if (ln_a || ln_b || dx_colsum) {
-    fused_param_reduce_kernel<<<a.c / 32, 256, 0, stream>>>(a.part, blocks, a.c, ln_a ? dga : nullptr, ln_a ? dba : nullptr,
-                                                            ln_b ? dgb : nullptr, ln_b ? dbb : nullptr, dx_colsum);
+    fused_param_reduce_kernel<<<dim3(a.c / 32, 5), 256, 0, stream>>>(a.part, blocks, a.c, ln_a ? dga : nullptr, ln_a ? dba : nullptr,
+                                                                     ln_b ? dgb : nullptr, ln_b ? dbb : nullptr, dx_colsum);
     count_launches(1);
   }
   B2PC_CHECK_LAUNCH("fused_residual_bwd");
@@ -410,6 +420,72 @@ gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t total
     };
     st4<T>(dx + i * 4, make_float4(g(v.x, d.x), g(v.y, d.y), g(v.z, d.z), g(v.w, d.w)));
   }
+}
+
+
+// GELU backward fused with the column sums of its result (= bias gradient of the Linear in front of the GELU, ptv3m1:238):
+// same tiling as colsum_partial_kernel (256-channel slabs x row chunks, 64 vector columns x 4 row lanes per block).
+template <typename T>
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t n, int c, int64_t rows_per_block, T* __restrict__ dx,
+                       float* __restrict__ partial) {
+  __shared__ float4 red[4][64];
+  const int cvi = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int ch = blockIdx.x * 256 + cvi * 4;
+  const int64_t r_begin = blockIdx.y * rows_per_block;
+  int64_t r_end = r_begin + rows_per_block;
+  if (r_end > n) r_end = n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto g = [](float t, float dd) {
+    const float cdf = 0.5f * (1.f + erff(t * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * t * t);
+    return dd * (cdf + t * pdf);
+  };
+  if (ch < c) {
+    for (int64_t r = r_begin + rl; r < r_end; r += 4) {
+      const float4 v = ld4<T>(x + r * c + ch), d = ld4<T>(dy + r * c + ch);
+      const float4 o = make_float4(g(v.x, d.x), g(v.y, d.y), g(v.z, d.z), g(v.w, d.w));
+      st4<T>(dx + r * c + ch, o);
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+  }
+  red[rl][cvi] = acc;
+  __syncthreads();
+  if (rl == 0 && ch < c) {
+    float4 t = red[0][cvi];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { t.x += red[i][cvi].x; t.y += red[i][cvi].y; t.z += red[i][cvi].z; t.w += red[i][cvi].w; }
+    *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.y * c + ch) = t;
+  }
+}
+
+inline int gelu_colsum_chunks(int64_t n, int c) {
+  const int slabs = (c + 255) / 256;
+  int64_t chunks = (4 * kNumSMs + slabs - 1) / slabs;
+  const int64_t max_chunks = ceil_div(n > 0 ? n : 1, 32);
+  if (chunks > max_chunks) chunks = max_chunks;
+  return (int)(chunks < 1 ? 1 : chunks);
+}
+inline size_t gelu_bwd_colsum_workspace_bytes(int64_t n, int c) { return (size_t)gelu_colsum_chunks(n, c) * c * sizeof(float) + 256; }
+
+inline int launch_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int64_t n, int c, void* dx, float* colsum_out, void* ws,
+                                  size_t ws_bytes, cudaStream_t stream) {
+  B2PC_CHECK_ARG(c % 4 == 0 && c > 0 && n >= 0, "gelu_bwd_colsum: bad sizes");
+  if (ws_bytes < gelu_bwd_colsum_workspace_bytes(n, c)) { set_error("gelu_bwd_colsum: workspace too small"); return B2PC_ERR_WORKSPACE; }
+  if (n == 0) { cudaMemsetAsync(colsum_out, 0, c * sizeof(float), stream); return B2PC_OK; }
+  const int chunks = gelu_colsum_chunks(n, c);
+  const int64_t rpb = ceil_div(ceil_div(n, chunks), 4) * 4;
+  dim3 grid((c + 255) / 256, chunks);
+  switch (dtype) {
+    case B2PC_F32: gelu_bwd_colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)dy, (const float*)x, n, c, rpb, (float*)dx, (float*)ws); break;
+    case B2PC_F16: gelu_bwd_colsum_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)dy, (const __half*)x, n, c, rpb, (__half*)dx, (float*)ws); break;
+    case B2PC_BF16: gelu_bwd_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, n, c, rpb, (__nv_bfloat16*)dx, (float*)ws); break;
+    default: set_error("gelu_bwd_colsum: unknown dtype %d", dtype); return B2PC_ERR_INVALID_ARG;
+  }
+  colsum_final_kernel<<<(c + 31) / 32, 256, 0, stream>>>((const float*)ws, chunks, c, colsum_out);
+  count_launches(2);
+  B2PC_CHECK_LAUNCH("gelu_bwd_colsum");
+  return B2PC_OK;
 }
 
 }  // namespace b2pc

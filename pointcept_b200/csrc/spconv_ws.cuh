@@ -179,18 +179,19 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
         cp_async4(dst + k * (kWsRows * 4), pair + (int64_t)kp * pair_stride + j, true);
       }
     };
-    uint32_t gi = 0;                    // units (incl. END markers) committed so far
+    uint32_t gi = 0, sig = 0;           // units (incl. END markers) committed / signalled full
     int st_i = 0, st_ph = 0;            // ring position of the next unit: stage and how often the ring wrapped (parity)
     int arr_i = 0;                      // stage of the next unit to be signalled full
     auto commit_unit = [&]() {          // close this unit's copy group; signal the unit LAG positions back, whose copies have landed
       cp_async_commit();
-      if (gi >= (uint32_t)LAG) {
+      ++gi;
+      if (gi - sig > (uint32_t)LAG) {
         cp_async_wait<LAG>();
         fence_proxy_async();
         mbar_arrive(&ctl->full[arr_i]);
         if (++arr_i == S) arr_i = 0;
+        ++sig;
       }
-      ++gi;
       if (++st_i == S) { st_i = 0; st_ph ^= 1; }
     };
     auto acquire_stage = [&]() {        // the MMAs that read this stage one ring turn ago have completed
@@ -263,12 +264,13 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
       // the next tile's slice was committed n_units groups before the END group: make sure it has landed (own row only)
       if (have_next && n_units < LAG) cp_async_wait_dyn(n_units);
     }
-    // drain: the last LAG units
+    // drain: the units still inside the LAG window
     cp_async_wait<0>();
     fence_proxy_async();
-    for (uint32_t u = gi >= (uint32_t)LAG ? gi - LAG : 0; u < gi; ++u) {
+    while (sig < gi) {
       mbar_arrive(&ctl->full[arr_i]);
       if (++arr_i == S) arr_i = 0;
+      ++sig;
     }
   } else if (warp == 8) {
     // ===================================== MMA issuer (whole warp waits, lane 0 issues) =====================================
@@ -511,18 +513,29 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
       const uint32_t dst = smem_u32(idx_s + (size_t)buf * kspan * kWg2Rows + r);
       for (int kk = h; kk < k_cnt; kk += 2) cp_async4(dst + kk * (kWg2Rows * 4), pair + (int64_t)(k_lo + kk) * pair_stride + j, true);
     };
-    uint32_t gi = 0;
+    uint32_t gi = 0, sig = 0;          // units committed / units signalled full
     int st_i = 0, st_ph = 0, arr_i = 0;
     auto commit_unit = [&]() {
       cp_async_commit();
-      if (gi >= (uint32_t)LAG) {
+      ++gi;
+      if (gi - sig > (uint32_t)LAG) {  // the copies of unit `sig` (LAG groups back) have landed
         cp_async_wait<LAG>();
         fence_proxy_async();
         mbar_arrive(&ctl->full[arr_i]);
         if (++arr_i == S) arr_i = 0;
+        ++sig;
       }
-      ++gi;
       if (++st_i == S) { st_i = 0; st_ph ^= 1; }
+    };
+    auto flush_signals = [&]() {       // signal everything committed so far (before waiting on MMA progress that may need it)
+      if (sig == gi) return;
+      cp_async_wait<0>();
+      fence_proxy_async();
+      while (sig < gi) {
+        mbar_arrive(&ctl->full[arr_i]);
+        if (++arr_i == S) arr_i = 0;
+        ++sig;
+      }
     };
     uint32_t chunk_local = 0;
     long long rc = split;
@@ -539,10 +552,15 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
       const bool row_ok = rc * kWg2Rows + r < n_out;
       const int32_t* my_idx = idx_s + (size_t)buf * kspan * kWg2Rows + r;
       for (int mt = 0; mt < n_mt; ++mt) {
-        if (gi >= (uint32_t)S) mbar_wait(&ctl->empty[st_i], st_ph ^ 1);
+        if (gi >= (uint32_t)S) mbar_wait(&ctl->empty[st_i], st_ph ^ 1);   // S > LAG: the unit one ring turn back is signalled
         if (mt == 0) {   // dout tile of this chunk (operand B, MN-major planes): rides in the first unit's copy group
           const int b = chunk_local % kWg2NB;
-          if (chunk_local >= (uint32_t)kWg2NB) mbar_wait(&ctl->bempty[b], ((chunk_local / kWg2NB) - 1) & 1);
+          if (chunk_local >= (uint32_t)kWg2NB) {
+            // the buffer frees when the MMAs of chunk (chunk_local - NB) are done; with few units per chunk those units may
+            // still sit un-signalled inside the LAG window -- signal them first, or producer and MMA warp wait on each other
+            if ((kWg2NB - 1) * n_mt < LAG) flush_signals();
+            mbar_wait(&ctl->bempty[b], ((chunk_local / kWg2NB) - 1) & 1);
+          }
           const int ppr = n_tile / 8;
           const uint32_t b_dst = smem_u32(b_ring + (size_t)b * b_bytes);
           for (int q = tid; q < kWg2Rows * ppr; q += 128) {
@@ -568,12 +586,7 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
       // the next chunk's slice was committed n_mt - 1 groups before the last unit: make sure this thread's part has landed
       if (have_next && n_mt - 1 < LAG) cp_async_wait_dyn(n_mt - 1);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (uint32_t u = gi >= (uint32_t)LAG ? gi - LAG : 0; u < gi; ++u) {
-      mbar_arrive(&ctl->full[arr_i]);
-      if (++arr_i == S) arr_i = 0;
-    }
+    flush_signals();
     // ===================================== epilogue (same warps; TMEM lane quarter = warp) =====================================
     mbar_wait(&ctl->done, 0);
     tc_fence_after();

@@ -444,12 +444,14 @@ struct FusedResidualFn : public torch::autograd::Function<FusedResidualFn> {
 
 // ---- exact GELU --------------------------------------------------------------------------------------------------------------------------
 struct GeluFn : public torch::autograd::Function<GeluFn> {
-  static Tensor forward(AutogradContext* ctx, Tensor x) {
+  // x_bias: bias of the Linear that produced x (entered that Linear detached); its gradient = column sums of dx, produced here
+  static Tensor forward(AutogradContext* ctx, Tensor x, c10::optional<Tensor> x_bias) {
     B2PC_GUARD(x);
     x = x.contiguous();
     Tensor y = at::empty_like(x);
     check(b2pc_gelu_fwd(x.data_ptr(), dt(x), x.numel(), y.data_ptr(), cur_stream()), "gelu_fwd");
     ctx->save_for_backward({x});
+    ctx->saved_data["xb_dtype"] = (x_bias.has_value() && x_bias->defined() && x.dim() == 2) ? (int64_t)x_bias->scalar_type() : (int64_t)-1;
     return y;
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
@@ -458,8 +460,20 @@ struct GeluFn : public torch::autograd::Function<GeluFn> {
     Tensor dy = grads[0].contiguous();
     if (dy.scalar_type() != x.scalar_type()) dy = dy.to(x.scalar_type());
     Tensor dx = at::empty_like(x);
-    check(b2pc_gelu_bwd(dy.data_ptr(), x.data_ptr(), dt(x), x.numel(), dx.data_ptr(), cur_stream()), "gelu_bwd");
-    return {dx};
+    const int64_t xbd = ctx->saved_data["xb_dtype"].toInt();
+    Tensor db;
+    if (xbd >= 0) {
+      const int64_t n = x.size(0), c = x.size(1);
+      db = at::empty({c}, x.options().dtype(at::kFloat));
+      Tensor ws = workspace(b2pc_gelu_bwd_colsum_workspace_bytes(n, (int)c), x);
+      check(b2pc_gelu_bwd_colsum(dy.data_ptr(), x.data_ptr(), dt(x), n, (int)c, dx.data_ptr(), db.data_ptr<float>(), ws.data_ptr(),
+                                 (size_t)ws.numel(), cur_stream()),
+            "gelu_bwd_colsum");
+      if ((at::ScalarType)xbd != at::kFloat) db = db.to((at::ScalarType)xbd);
+    } else {
+      check(b2pc_gelu_bwd(dy.data_ptr(), x.data_ptr(), dt(x), x.numel(), dx.data_ptr(), cur_stream()), "gelu_bwd");
+    }
+    return {dx, db};
   }
 };
 
@@ -540,7 +554,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                              c10::optional<Tensor> x_bias) {
     return FusedResidualFn::apply(shortcut, x, u, keep, ga, ba, eps_a, gb, bb, eps_b, emit_half, x_bias);
   });
-  m.def("gelu", [](Tensor x) { return GeluFn::apply(x); });
+  m.def("gelu", [](Tensor x, c10::optional<Tensor> x_bias) { return GeluFn::apply(x, x_bias); }, py::arg("x"), py::arg("x_bias") = py::none());
   m.def("serialized_attention", [](Tensor qkv, Tensor gidx, Tensor sidx, Tensor dup_point, Tensor cu, int64_t max_seqlen, int64_t heads,
                                    double scale) { return SerializedAttentionFn::apply(qkv, gidx, sidx, dup_point, cu, max_seqlen, heads, scale); });
   m.def("make_cast_plan", &make_cast_plan);

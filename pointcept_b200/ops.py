@@ -582,12 +582,19 @@ def fused_residual_supported(x, c):
     return binding() is not None and x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and c in (32, 64, 128, 256, 512)
 
 
-def gelu(x):
-    """exact (erf) GELU, one kernel per direction through the compiled binding; torch otherwise."""
+def gelu(x, x_bias=None):
+    """exact (erf) GELU, one kernel per direction through the compiled binding; torch otherwise.
+    x_bias: bias of the Linear that produced x when it entered that Linear detached: its gradient (column sums of the GELU
+    backward's result) then comes out of the same kernel that computes that result."""
     B = binding()
     if B is not None and x.is_cuda and x.dtype in _DTYPES and x.numel() % 4 == 0:
-        return B.gelu(x)
+        return B.gelu(x, x_bias)
+    assert x_bias is None
     return torch.nn.functional.gelu(x)
+
+
+def gelu_fused_ok(x):
+    return binding() is not None and x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and x.shape[1] % 4 == 0
 
 
 class HalfShadows:

@@ -227,8 +227,13 @@ class MLP(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, fc2_bias_grad_elsewhere=False):
-        h = self.fc1(x)
-        h = ops.gelu(h) if (type(self.act) is nn.GELU and self.act.approximate == "none") else self.act(h)
+        exact_gelu = type(self.act) is nn.GELU and self.act.approximate == "none"
+        if exact_gelu and self.fc1.bias is not None and ops.gelu_fused_ok(x) and isinstance(self.fc1, FusedLinear):
+            # fc1's bias gradient = column sums of the GELU backward's result: produced by that kernel, no separate reduction
+            h = ops.gelu(self.fc1(x, bias_grad_elsewhere=True), self.fc1.bias)
+        else:
+            h = self.fc1(x)
+            h = ops.gelu(h) if exact_gelu else self.act(h)
         if fc2_bias_grad_elsewhere and self.drop.p == 0.0:
             return self.fc2(h, bias_grad_elsewhere=True)
         return self.drop(self.fc2(self.drop(h)))

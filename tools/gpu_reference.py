@@ -68,7 +68,7 @@ class _NativeConvFn(torch.autograd.Function):
         return dfeat, dw.to(ctx.wdtype), db, None
 
 
-def native_sparse_conv(feat, weight, bias, table_fwd, table_bwd, flip_bwd):
+def native_sparse_conv(feat, weight, bias, table_fwd, table_bwd, flip_bwd, w16=None, b16=None):
     return _NativeConvFn.apply(feat, weight, bias, table_fwd)
 
 

@@ -57,10 +57,17 @@ struct ProfScope {
 }  // namespace
 #define B2PC_PROF(stream, id, flops, bytes) ProfScope prof_scope__((stream), (id), (double)(flops), (double)(bytes))
 
-// B2PC_CONV_V1=1 selects the first-generation (round 1) tcgen05 sparse-conv kernels for A/B runs
+// Sparse-conv kernel generations (A/B switches).  Weight gradient: the warp-specialised persistent kernel (wgrad_ws_kernel) is the
+// default, B2PC_CONV_V1=1 selects the round-1 kernel.  Forward / backward-data: the round-1 output-stationary kernel
+// (gather_gemm_umma_kernel, 4 CTAs per SM) is still the faster one on B200 (profiles/README.md) and stays the default;
+// B2PC_CONV_WS=1 selects the warp-specialised conv_ws_kernel.
 static bool conv_v1() {
   static const bool v = [] { const char* e = getenv("B2PC_CONV_V1"); return e && atoi(e) != 0; }();
   return v;
+}
+static bool conv_fwd_ws() {
+  static const bool v = [] { const char* e = getenv("B2PC_CONV_WS"); return e && atoi(e) != 0; }();
+  return v && !conv_v1();
 }
 
 extern "C" {
@@ -175,7 +182,7 @@ int b2pc_rulebook_strided_finish(const int32_t* indices, int64_t n, const int* s
 // ---- sparse convolution arithmetic ---------------------------------------------------------------------
 size_t b2pc_spconv_gather_gemm_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
 #ifndef B2PC_NO_UMMA
-  if (!conv_v1()) return 0;
+  if (conv_fwd_ws()) return 0;
   return conv_umma_workspace_bytes(n_out, c_in, c_out, kv);
 #else
   return 0;
@@ -192,7 +199,7 @@ int b2pc_spconv_gather_gemm(const void* feat, const void* weight, const void* bi
   cudaStream_t s = (cudaStream_t)stream;
 #ifndef B2PC_NO_UMMA
   if (impl != 1) {
-    if (!conv_v1() && conv_ws_supported(dtype, c_in, c_out, kv))
+    if (conv_fwd_ws() && conv_ws_supported(dtype, c_in, c_out, kv))
       return launch_conv_ws(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, dtype, out, s);
     if (spconv_umma_supported(dtype, c_in, c_out)) {
       const size_t need = conv_umma_workspace_bytes(n_out, c_in, c_out, kv);

@@ -8,6 +8,8 @@ import time
 import numpy as np
 import torch
 
+os.environ.setdefault("B2PC_CONV_WS", "1")    # sweep the warp-specialised forward kernel too (not the default)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pointcept_b200 import ops, synth  # noqa: E402
 

@@ -10,8 +10,10 @@ done
 grep -E "largest|zero ref|autocast torch|GradScaler" gpurun_out/pytest_test_gpu_model.log | cut -c1-500
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 # ncu --set full of the two warp-specialised conv kernels (C=32, N=240k) for offline analysis
-B2PC_CONV_WS=1 ONLY=0 IMPLS=2 timeout 400 ncu --set full --clock-control none --import-source on -k "regex:conv_ws_kernel|wgrad_ws_kernel" -s 8 -c 2 -f -o gpurun_out/r02_conv_ws_c32 \
+B2PC_CONV_WS=1 ONLY=0 IMPLS=2 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_ws_kernel -s 4 -c 1 -f -o gpurun_out/r02_conv_ws_c32 \
    python tools/probe_conv.py > gpurun_out/ncu_conv.log 2>&1; tail -2 gpurun_out/ncu_conv.log | cut -c1-200
+ONLY=0 IMPLS=2 timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad_ws_kernel -s 2 -c 1 -f -o gpurun_out/r02_wgrad_ws_c32 \
+   python tools/probe_conv.py > gpurun_out/ncu_wgrad.log 2>&1; tail -2 gpurun_out/ncu_wgrad.log | cut -c1-200
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 2600 --csv --log-file gpurun_out/r02_launches.csv \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-supplementary --no-gpu-reference > gpurun_out/ncu_bench.log 2>&1
 tail -1 gpurun_out/ncu_bench.log | cut -c1-200

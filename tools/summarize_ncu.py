@@ -16,7 +16,11 @@ WANT = ['Kernel Name', 'launch__grid_size', 'gpu__time_duration.sum', 'dram__byt
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'launch__block_size', 'smsp__inst_executed.sum']
 
 
 def full(rep, out, header):
@@ -57,11 +61,10 @@ def launches(csv_path, out, header):
 
 
 if __name__ == "__main__":
-    launches("gpurun_out/r01_launches.csv", "profiles/r01_ncu_launch_summary.txt",
-             "# ncu launch list of one PT-v3m1-base training step (2 x 120k-voxel scenes): bench.py --steps 2 --warmup 3 under\n"
-             "# ncu --metrics gpu__time_duration.sum --clock-control none -s 8000 -c 2700 (cold-cache, serialised: compare SHARES)")
-    full("gpurun_out/r01_ncu_attn.ncu-rep", "profiles/r01_ncu_attention_full_metrics.txt",
-         "# ncu --set full --clock-control none, tools/probe_attn.py time (H=2, T=241664, K=1024, bf16): attn_fwd_umma_kernel (TMA path)")
-    full("gpurun_out/r01_ncu_conv.ncu-rep", "profiles/r01_ncu_conv_full_metrics.txt",
-         "# ncu --set full --clock-control none, tools/probe_conv.py ONLY=0 (N=240000, C=32->32, 3^3, rows in shuffled order): "
-         "gather_gemm_umma_kernel fwd, bwd-data, then bwd_weight_umma_kernel")
+    import os
+    if len(sys.argv) >= 4 and sys.argv[1] == "full":          # python tools/summarize_ncu.py full <rep> <out> "<header>"
+        full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "# ncu --set full")
+    elif len(sys.argv) >= 4 and sys.argv[1] == "launches":    # python tools/summarize_ncu.py launches <csv> <out> "<header>"
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "# ncu launch list")
+    else:
+        print(__doc__)

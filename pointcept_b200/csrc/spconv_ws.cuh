@@ -114,7 +114,7 @@ static_assert(sizeof(WsCtrl) <= kWsCtrlBytes, "control block too large");
 // KC/8 cp.async from ONE base pointer -- the leanest instruction stream per gathered byte, which is what bounds this kernel
 // (ncu: with one warp per scheduler the producers are issue-latency bound).  The rulebook slice of the NEXT tile is fetched by
 // 4-byte cp.async into a second shared-memory buffer while the current tile's rows stream, so no index load is ever exposed.
-template <typename T, int KC, int LAG>
+template <typename T, int KC, int LAG /* unused: hand-over is wait-free */>
 __global__ void __launch_bounds__(kWsThreads, 1)
 conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
@@ -135,7 +135,7 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
 
   if (warp == 0) { tmem_alloc(&ctl->tmem_slot, cfg.tmem_cols); tmem_relinquish(); }
   if (tid == 32) {
-    for (int s = 0; s < S; ++s) { mbar_init(&ctl->full[s], 128); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&ctl->full[s], 129); mbar_init(&ctl->empty[s], 1); }   // 128 copy-tracking arrivals + 1
     for (int b = 0; b < 2; ++b) { mbar_init(&ctl->acc_full[b], 1); mbar_init(&ctl->acc_empty[b], 128); }
     for (int i = 0; i < 12; ++i) (&ctl->mask_x[0][0])[i] = 0;
     fence_mbar_init();
@@ -179,19 +179,18 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
         cp_async4(dst + k * (kWsRows * 4), pair + (int64_t)kp * pair_stride + j, true);
       }
     };
-    uint32_t gi = 0, sig = 0;           // units (incl. END markers) committed / signalled full
-    int st_i = 0, st_ph = 0;            // ring position of the next unit: stage and how often the ring wrapped (parity)
-    int arr_i = 0;                      // stage of the next unit to be signalled full
-    auto commit_unit = [&]() {          // close this unit's copy group; signal the unit LAG positions back, whose copies have landed
-      cp_async_commit();
-      ++gi;
-      if (gi - sig > (uint32_t)LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async();
-        mbar_arrive(&ctl->full[arr_i]);
-        if (++arr_i == S) arr_i = 0;
-        ++sig;
+    uint32_t gi = 0;                    // units (incl. END markers) produced so far
+    int st_i = 0, st_ph = 0;            // ring position of the next unit: stage and ring-turn parity
+    // A unit is handed over without any wait on the producer side: every thread lets the stage's `full` barrier track its own
+    // outstanding copies (cp.async.mbarrier.arrive.noinc: the arrival fires when they have landed), thread 0 adds one ordinary
+    // (releasing) arrival after writing the unit's descriptor word.  Copies of up to S units are in flight per thread.
+    auto publish_unit = [&](uint32_t meta_word) {
+      cp_async_mbar_arrive_noinc(&ctl->full[st_i]);
+      if (ptid == 0) {
+        ctl->meta[st_i] = meta_word;
+        mbar_arrive(&ctl->full[st_i]);
       }
+      ++gi;
       if (++st_i == S) { st_i = 0; st_ph ^= 1; }
     };
     auto acquire_stage = [&]() {        // the MMAs that read this stage one ring turn ago have completed
@@ -202,12 +201,13 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
     if (item < n_items) {
       fetch_idx(item, 0);
       cp_async_commit();
-      cp_async_wait<0>();
     }
     for (; item < n_items; item += gridDim.x, ++tcount) {
       const int buf = tcount & 1, slot = tcount % 3;
       const int32_t* my_idx = idx_s + (size_t)buf * kv * kWsRows + ptid;
       const bool row_ok = (item / n_ntiles) * kWsRows + ptid < n_out;
+      // this tile's rulebook slice was committed (as a copy group of its own) one whole tile ago
+      cp_async_wait<0>();
       // ---- which offsets have a partner anywhere in this tile ----
       for (int k = 0; k < kv; ++k) {
         const bool v = row_ok && my_idx[k * kWsRows] >= 0;
@@ -234,12 +234,10 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
       }
       if (n_act == 0) { if (ptid == 0) act[0] = 0; n_act = 1; }   // a tile always carries at least one (all-zero) unit
       named_bar_sync(1, 128);
-      // ---- next tile's rulebook slice rides in the copy group of this tile's first unit ----
-      const bool have_next = item + gridDim.x < n_items;
-      if (have_next) fetch_idx(item + gridDim.x, buf ^ 1);
+      // ---- next tile's rulebook slice: its own copy group (together with the previous tile's, long finished, row copies) ----
+      if (item + gridDim.x < n_items) fetch_idx(item + gridDim.x, buf ^ 1);
+      cp_async_commit();
       const int n0 = (int)(item % n_ntiles) * n_tile;
-      const int n_units = n_act * n_cc;
-      bool first = true;
       for (int a = 0; a < n_act; ++a) {
         const int kidx = act[a];
         const int32_t src = row_ok ? my_idx[kidx * kWsRows] : -1;
@@ -251,26 +249,12 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
 #pragma unroll
           for (int p = 0; p < LPR; ++p) cp_async16(a_dst + p * (kWsRows * 16), g + cc * KC + p * 8, src >= 0);
           if (!resident) load_w_tile(a_s + a_bytes, kidx, cc, n0, ptid, 128);
-          if (ptid == 0) ctl->meta[st_i] = (uint32_t)kidx | ((uint32_t)cc << 10);
-          commit_unit();
-          first = false;
+          publish_unit((uint32_t)kidx | ((uint32_t)cc << 10));
         }
       }
-      (void)first;
       // END marker: the MMA thread hands the accumulator to the epilogue warps
       acquire_stage();
-      if (ptid == 0) ctl->meta[st_i] = kMetaEnd;
-      commit_unit();
-      // the next tile's slice was committed n_units groups before the END group: make sure it has landed (own row only)
-      if (have_next && n_units < LAG) cp_async_wait_dyn(n_units);
-    }
-    // drain: the units still inside the LAG window
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (sig < gi) {
-      mbar_arrive(&ctl->full[arr_i]);
-      if (++arr_i == S) arr_i = 0;
-      ++sig;
+      publish_unit(kMetaEnd);
     }
   } else if (warp == 8) {
     // ===================================== MMA issuer (whole warp waits, lane 0 issues) =====================================
@@ -296,6 +280,7 @@ conv_ws_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T
         }
         if (first && ause > 0) mbar_wait(&ctl->acc_empty[buf], (ause - 1) & 1);   // epilogue drained this buffer
         if (lane == 0) {
+          fence_proxy_async();     // the stage was filled by cp.async (generic proxy); tcgen05.mma reads it through the async proxy
           tc_fence_after();
           const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
           const int kidx = m & 0x3FF, cc = (m >> 10) & 0x3FF;
@@ -363,8 +348,7 @@ inline int launch_conv_ws_t(const void* feat, const void* weight, const void* bi
                             int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, void* out, cudaStream_t stream) {
   const ConvWsCfg c = conv_ws_cfg(n_out, c_in, c_out, kv);
 #define B2PC_WS_GO(KC_, LAG_) launch_conv_ws_kc<T, KC_, LAG_>(c, feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, stream)
-  if (c.lag == 6) { if (c.kc == 64) B2PC_WS_GO(64, 6); else if (c.kc == 32) B2PC_WS_GO(32, 6); else B2PC_WS_GO(16, 6); }
-  else { if (c.kc == 64) B2PC_WS_GO(64, 2); else if (c.kc == 32) B2PC_WS_GO(32, 2); else B2PC_WS_GO(16, 2); }
+  if (c.kc == 64) B2PC_WS_GO(64, 0); else if (c.kc == 32) B2PC_WS_GO(32, 0); else B2PC_WS_GO(16, 0);
 #undef B2PC_WS_GO
   count_launches(1);
   B2PC_CHECK_LAUNCH("spconv_gather_gemm(tcgen05, warp-specialised)");
@@ -513,54 +497,27 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
       const uint32_t dst = smem_u32(idx_s + (size_t)buf * kspan * kWg2Rows + r);
       for (int kk = h; kk < k_cnt; kk += 2) cp_async4(dst + kk * (kWg2Rows * 4), pair + (int64_t)(k_lo + kk) * pair_stride + j, true);
     };
-    uint32_t gi = 0, sig = 0;          // units committed / units signalled full
-    int st_i = 0, st_ph = 0, arr_i = 0;
-    auto commit_unit = [&]() {
-      cp_async_commit();
-      ++gi;
-      if (gi - sig > (uint32_t)LAG) {  // the copies of unit `sig` (LAG groups back) have landed
-        cp_async_wait<LAG>();
-        fence_proxy_async();
-        mbar_arrive(&ctl->full[arr_i]);
-        if (++arr_i == S) arr_i = 0;
-        ++sig;
-      }
-      if (++st_i == S) { st_i = 0; st_ph ^= 1; }
-    };
-    auto flush_signals = [&]() {       // signal everything committed so far (before waiting on MMA progress that may need it)
-      if (sig == gi) return;
-      cp_async_wait<0>();
-      fence_proxy_async();
-      while (sig < gi) {
-        mbar_arrive(&ctl->full[arr_i]);
-        if (++arr_i == S) arr_i = 0;
-        ++sig;
-      }
-    };
+    uint32_t gi = 0;
+    int st_i = 0, st_ph = 0;
     uint32_t chunk_local = 0;
     long long rc = split;
     if (rc < n_rc) {
       fetch_idx(rc, 0);
       cp_async_commit();
-      cp_async_wait<0>();
     }
     for (; rc < n_rc; rc += n_splits, ++chunk_local) {
       const int buf = chunk_local & 1;
-      named_bar_sync(1, 128);                      // the other half-row thread's index copies are visible; previous chunk fully issued
-      const bool have_next = rc + n_splits < n_rc;
-      if (have_next) fetch_idx(rc + n_splits, buf ^ 1);
+      cp_async_wait<0>();                          // this chunk's rulebook slice (own copy group, committed one chunk ago) has landed
+      named_bar_sync(1, 128);                      // ... and so has the half fetched by the other thread of this row
+      if (rc + n_splits < n_rc) fetch_idx(rc + n_splits, buf ^ 1);
+      cp_async_commit();
       const bool row_ok = rc * kWg2Rows + r < n_out;
       const int32_t* my_idx = idx_s + (size_t)buf * kspan * kWg2Rows + r;
       for (int mt = 0; mt < n_mt; ++mt) {
-        if (gi >= (uint32_t)S) mbar_wait(&ctl->empty[st_i], st_ph ^ 1);   // S > LAG: the unit one ring turn back is signalled
-        if (mt == 0) {   // dout tile of this chunk (operand B, MN-major planes): rides in the first unit's copy group
+        if (gi >= (uint32_t)S) mbar_wait(&ctl->empty[st_i], st_ph ^ 1);
+        if (mt == 0) {   // dout tile of this chunk (operand B, MN-major planes): tracked by the first unit's barrier
           const int b = chunk_local % kWg2NB;
-          if (chunk_local >= (uint32_t)kWg2NB) {
-            // the buffer frees when the MMAs of chunk (chunk_local - NB) are done; with few units per chunk those units may
-            // still sit un-signalled inside the LAG window -- signal them first, or producer and MMA warp wait on each other
-            if ((kWg2NB - 1) * n_mt < LAG) flush_signals();
-            mbar_wait(&ctl->bempty[b], ((chunk_local / kWg2NB) - 1) & 1);
-          }
+          if (chunk_local >= (uint32_t)kWg2NB) mbar_wait(&ctl->bempty[b], ((chunk_local / kWg2NB) - 1) & 1);
           const int ppr = n_tile / 8;
           const uint32_t b_dst = smem_u32(b_ring + (size_t)b * b_bytes);
           for (int q = tid; q < kWg2Rows * ppr; q += 128) {
@@ -581,12 +538,12 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
           ++slot;
           if (++cchunk == n_cc) { cchunk = 0; ++k; }
         }
-        commit_unit();
+        // hand-over without a wait: the stage's barrier tracks this thread's outstanding copies (arrival fires when they landed)
+        cp_async_mbar_arrive_noinc(&ctl->full[st_i]);
+        ++gi;
+        if (++st_i == S) { st_i = 0; st_ph ^= 1; }
       }
-      // the next chunk's slice was committed n_mt - 1 groups before the last unit: make sure this thread's part has landed
-      if (have_next && n_mt - 1 < LAG) cp_async_wait_dyn(n_mt - 1);
     }
-    flush_signals();
     // ===================================== epilogue (same warps; TMEM lane quarter = warp) =====================================
     mbar_wait(&ctl->done, 0);
     tc_fence_after();
@@ -622,6 +579,7 @@ wgrad_ws_kernel(const T* __restrict__ feat, const T* __restrict__ dout, const in
         mbar_wait(&ctl->full[s], st_ph);
         if (++st_i == S) { st_i = 0; st_ph ^= 1; }
         if (lane == 0) {
+          fence_proxy_async();     // operands were written by cp.async (generic proxy), tcgen05.mma reads through the async proxy
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_ring + (size_t)s * a_bytes);
 #pragma unroll
@@ -657,11 +615,7 @@ inline int launch_wgrad_ws_t(const void* feat, const void* dout, const int32_t* 
   const WgradWsCfg c = wgrad_ws_cfg(n_out, c_in, c_out, kv);
   float* dst = c.n_splits > 1 ? (float*)ws : dweight;
 #define B2PC_WG_GO(MC_, LAG_) launch_wgrad_ws_mc<T, MC_, LAG_>(c, feat, dout, pair, pair_stride, n_out, c_in, c_out, kv, dst, stream)
-  if (c.lag == 6) {
-    switch (c.mc) { case 128: B2PC_WG_GO(128, 6); break; case 64: B2PC_WG_GO(64, 6); break; case 32: B2PC_WG_GO(32, 6); break; default: B2PC_WG_GO(16, 6); }
-  } else {
-    switch (c.mc) { case 128: B2PC_WG_GO(128, 2); break; case 64: B2PC_WG_GO(64, 2); break; case 32: B2PC_WG_GO(32, 2); break; default: B2PC_WG_GO(16, 2); }
-  }
+  switch (c.mc) { case 128: B2PC_WG_GO(128, 0); break; case 64: B2PC_WG_GO(64, 0); break; case 32: B2PC_WG_GO(32, 0); break; default: B2PC_WG_GO(16, 0); }
 #undef B2PC_WG_GO
   count_launches(1);
   if (c.n_splits > 1) {

@@ -164,6 +164,10 @@ __device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc, b
 __device__ __forceinline__ void red_add_v4(float* gdst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gdst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// the mbarrier gets one arrival (already counted in its init value: .noinc) when every cp.async this thread issued so far has landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;

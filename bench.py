@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--gpu-reference-steps", type=int, default=5)
     ap.add_argument("--bucket-mb", type=int, default=100, help="DDP gradient bucket size")
     ap.add_argument("--no-static-graph", action="store_true", help="DDP without static_graph")
+    ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of pointcept_b200.optim.FusedAdamW")
     return ap.parse_args()
 
 
@@ -248,7 +249,11 @@ def measure(args, workload, scenes, voxels, steps, warmup, kind="indoor", want_p
     if world > 1 and not reference_stack:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True,
                                                         bucket_cap_mb=args.bucket_mb, static_graph=not args.no_static_graph)
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+    if reference_stack or args.torch_adamw:
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+    else:
+        from pointcept_b200.optim import FusedAdamW      # same update rule, one launch for all 486 tensors
+        opt = FusedAdamW(net.parameters(), lr=1e-4, weight_decay=0.05)
     hb = synth.make_batch(scenes, seed=100 + rank, target_voxels=voxels, kind=kind, num_classes=n_cls)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in hb.items()}
     offset_host = [int(v) for v in hb["offset"]]

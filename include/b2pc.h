@@ -244,6 +244,13 @@ int b2pc_fused_residual_bwd(const float* dr_out, const void* dr16, const void* d
  * long long count; long long first_block} with first_block the running sum of ceil(count / 2048); total_blocks its end. */
 int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks, int dst_dtype, b2pc_stream_t stream);
 
+/* AdamW (torch.optim.AdamW semantics: decoupled weight decay, per-tensor bias correction) over a whole parameter list in one
+ * launch.  items: DEVICE array of n_items 56-byte records {float* p; const float* g; float* m; float* v; long long count;
+ * long long first_block; float bc1; float bc2_sqrt} with first_block the running sum of ceil(count / 2048), bc1 = 1 - beta1^t and
+ * bc2_sqrt = sqrt(1 - beta2^t) for the tensor's own step count t; gradients are multiplied by grad_scale first. */
+int b2pc_multi_adamw(const void* items_device, int n_items, long long total_blocks, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, float grad_scale, b2pc_stream_t stream);
+
 /* Exact (erf) GELU over n_elems values (n_elems % 4 == 0), forward and backward (nn.GELU, point_transformer_v3m1_base.py:233). */
 int b2pc_gelu_fwd(const void* x, int dtype, int64_t n_elems, void* y, b2pc_stream_t stream);
 int b2pc_gelu_bwd(const void* dy, const void* x, int dtype, int64_t n_elems, void* dx, b2pc_stream_t stream);

@@ -397,6 +397,12 @@ int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks
   return launch_multi_cast(plan_device, n_items, total_blocks, dst_dtype, (cudaStream_t)stream);
 }
 
+int b2pc_multi_adamw(const void* items_device, int n_items, long long total_blocks, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, float grad_scale, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
+  return launch_multi_adamw(items_device, n_items, total_blocks, lr, beta1, beta2, eps, weight_decay, grad_scale, (cudaStream_t)stream);
+}
+
 static int gelu_grid(int64_t total4) {
   int64_t b = ceil_div(total4 > 0 ? total4 : 1, 256);
   return (int)(b > kNumSMs * 16 ? kNumSMs * 16 : b);

@@ -488,4 +488,61 @@ inline int launch_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int6
   return B2PC_OK;
 }
 
+
+// ---- AdamW over a whole parameter list in ONE launch (SURVEY.md 8(f).2 "fused AdamW behind the all-reduce") ---------------------
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction), fp32 parameters / gradients / moments:
+//   p *= 1 - lr*wd;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+// items[i] = {p, g, m, v, count, first_block, bc1 = 1 - b1^t, sqrt(bc2 = 1 - b2^t)} with t the tensor's own step count;
+// a block updates 2048 consecutive elements of one tensor.
+struct AdamItem { float* p; const float* g; float* m; float* v; long long count; long long first_block; float bc1; float bc2_sqrt; };
+
+__global__ void __launch_bounds__(256)
+multi_adamw_kernel(const AdamItem* __restrict__ items, int n_items, float lr, float b1, float b2, float eps, float wd, float grad_scale) {
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const AdamItem it = items[lo];
+  const long long base = ((long long)blockIdx.x - it.first_block) * kCastBlockElems;
+  const float step = lr / it.bc1, decay = 1.f - lr * wd, bc2_sqrt = it.bc2_sqrt;   // per-tensor bias correction (own step count)
+  const bool vec = ((reinterpret_cast<uintptr_t>(it.p) | reinterpret_cast<uintptr_t>(it.g) | reinterpret_cast<uintptr_t>(it.m) |
+                     reinterpret_cast<uintptr_t>(it.v)) & 15) == 0;
+  auto upd = [&](float& p, float g, float& m, float& v) {
+    g *= grad_scale;
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
+    p = p * decay - step * m / (sqrtf(v) / bc2_sqrt + eps);
+  };
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const long long i = base + (e * 256 + threadIdx.x) * 4;
+    if (i >= it.count) continue;
+    if (vec && i + 4 <= it.count) {
+      float4 p = *reinterpret_cast<float4*>(it.p + i), m = *reinterpret_cast<float4*>(it.m + i), v = *reinterpret_cast<float4*>(it.v + i);
+      const float4 g = *reinterpret_cast<const float4*>(it.g + i);
+      upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+      *reinterpret_cast<float4*>(it.p + i) = p;
+      *reinterpret_cast<float4*>(it.m + i) = m;
+      *reinterpret_cast<float4*>(it.v + i) = v;
+    } else {
+      for (long long j = i; j < i + 4 && j < it.count; ++j) {
+        float p = it.p[j], m = it.m[j], v = it.v[j];
+        upd(p, it.g[j], m, v);
+        it.p[j] = p; it.m[j] = m; it.v[j] = v;
+      }
+    }
+  }
+}
+
+inline int launch_multi_adamw(const void* items, int n_items, long long total_blocks, float lr, float b1, float b2, float eps, float wd,
+                              float grad_scale, cudaStream_t stream) {
+  B2PC_CHECK_ARG(items && n_items >= 0 && total_blocks >= 0, "multi_adamw: bad arguments");
+  if (n_items == 0 || total_blocks == 0) return B2PC_OK;
+  multi_adamw_kernel<<<(unsigned)total_blocks, 256, 0, stream>>>((const AdamItem*)items, n_items, lr, b1, b2, eps, wd, grad_scale);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("multi_adamw");
+  return B2PC_OK;
+}
+
 }  // namespace b2pc

@@ -597,6 +597,15 @@ def gelu_fused_ok(x):
     return binding() is not None and x.is_cuda and x.dim() == 2 and x.dtype in _DTYPES and x.shape[1] % 4 == 0
 
 
+_param_epoch = 0
+
+
+def bump_param_epoch():
+    """Called by writers that modify parameters through raw pointers (optim.FusedAdamW): shadows handed out before are stale."""
+    global _param_epoch
+    _param_epoch += 1
+
+
 class HalfShadows:
     """Half-precision shadows of the fp32 parameters that feed GEMM-shaped kernels (Linear and sparse-conv weights / biases).
     autocast re-casts every weight on every forward with one kernel each (~250 launches per PT-v3 step); here ONE launch
@@ -648,22 +657,22 @@ class HalfShadows:
             self._plan = B.make_cast_plan([p.detach() for p in params], shadows)
             self._key, self._ver = key, None
             self._flat = flat
-        ver = sum(p._version for p in params)
+        ver = (sum(p._version for p in params), _param_epoch)
         if ver != self._ver:
             B.run_cast_plan(self._plan[0], self._plan[1], self._plan[2], _DTYPES[dtype])
             self._ver = ver
             for m in mods:
-                m._w16_ver = m.weight._version
-                m._b16_ver = m.bias._version if m.bias is not None else -1
+                m._w16_ver = (m.weight._version, _param_epoch)
+                m._b16_ver = (m.bias._version, _param_epoch) if m.bias is not None else None
 
 
 def shadow_of(module, dtype):
     """(w16, b16) of a module managed by HalfShadows if they are current for `dtype`, else (None, None)."""
     w16 = getattr(module, "_w16", None)
-    if w16 is None or w16.dtype != dtype or getattr(module, "_w16_ver", -2) != module.weight._version:
+    if w16 is None or w16.dtype != dtype or getattr(module, "_w16_ver", None) != (module.weight._version, _param_epoch):
         return None, None
     b16 = getattr(module, "_b16", None)
-    if module.bias is not None and (b16 is None or getattr(module, "_b16_ver", -2) != module.bias._version):
+    if module.bias is not None and (b16 is None or getattr(module, "_b16_ver", None) != (module.bias._version, _param_epoch)):
         return None, None
     return w16, b16
 

@@ -387,7 +387,7 @@ def rooflines(prof, prof_ms_total, pk):
     tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath))
+            traffic = {k: v for k, v in json.load(open(tpath)).items() if not k.startswith("_")}
         except Exception:
             traffic = {}
     for name, r in prof.items():

@@ -140,24 +140,82 @@ def serialized_scatter_back(x_pad, primary_pos):
     return _SerializedScatterBack.apply(x_pad, primary_pos)
 
 
+class RPE(nn.Module):
+    """Relative position bias of the non-flash branch (ptv3m1:29-48): per-axis tables indexed by the clamped grid offset of every
+    (query, key) pair of a patch, summed over the three axes.  Parameter name and shape as in the reference (checkpoint ABI)."""
+
+    def __init__(self, patch_size, num_heads):
+        super().__init__()
+        self.patch_size, self.num_heads = patch_size, num_heads
+        self.pos_bnd = int((4 * patch_size) ** (1 / 3) * 2)
+        self.rpe_num = 2 * self.pos_bnd + 1
+        self.rpe_table = nn.Parameter(torch.zeros(3 * self.rpe_num, num_heads))
+        nn.init.trunc_normal_(self.rpe_table, std=0.02)
+
+    def forward(self, rel):                                                   # rel [P, K, K, 3] integer grid offsets
+        axis_base = torch.arange(3, device=rel.device) * self.rpe_num
+        rows = rel.clamp(-self.pos_bnd, self.pos_bnd) + self.pos_bnd + axis_base
+        bias = self.rpe_table.index_select(0, rows.reshape(-1)).view(rows.shape + (-1,)).sum(3)   # [P, K, K, H]
+        return bias.permute(0, 3, 1, 2)
+
+
 class SerializedAttention(PointModule):
-    """ptv3m1:51-222 (flash branch only: RPE / upcast options belong to the non-flash fallback)."""
+    """ptv3m1:51-222.  enable_flash=True (every stock config) is the operator path of this library; enable_flash=False is the
+    reference's own eager branch (dense per-patch softmax with optional RPE bias and fp32 upcasts, ptv3m1:173-206) -- there is no
+    third-party operator behind it in the reference either, so it is mirrored with the same torch ops on the patch tables
+    built by the library."""
 
     def __init__(self, channels, num_heads, patch_size, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0,
                  order_index=0, enable_rpe=False, enable_flash=True, upcast_attention=False, upcast_softmax=False):
         super().__init__()
         assert channels % num_heads == 0
-        if not enable_flash or enable_rpe or upcast_attention or upcast_softmax:
-            raise NotImplementedError("pointcept_b200 implements the enable_flash=True attention path only")
-        if attn_drop != 0.0:
-            raise NotImplementedError("attn_drop > 0 is not supported (all PT-v3 configs use 0.0)")
+        self.enable_flash, self.enable_rpe = enable_flash, enable_rpe
+        self.upcast_attention, self.upcast_softmax = upcast_attention, upcast_softmax
+        if enable_flash:
+            assert not enable_rpe, "Set enable_rpe to False when enable Flash Attention"
+            assert not upcast_attention, "Set upcast_attention to False when enable Flash Attention"
+            assert not upcast_softmax, "Set upcast_softmax to False when enable Flash Attention"
+            if attn_drop != 0.0:
+                raise NotImplementedError("attn_drop > 0 is not supported on the operator path (all PT-v3 configs use 0.0)")
+            self.patch_size = patch_size
+        else:
+            self.patch_size_max, self.patch_size = patch_size, 0      # set per call to min(patch_size_max, smallest scene)
+            self.attn_drop = nn.Dropout(attn_drop)
+            self.softmax = nn.Softmax(dim=-1)
         self.channels, self.num_heads = channels, num_heads
         self.scale = qk_scale or (channels // num_heads) ** -0.5
         self.order_index = order_index
-        self.patch_size = patch_size
         self.qkv = FusedLinear(channels, channels * 3, bias=qkv_bias)
         self.proj = FusedLinear(channels, channels)
         self.proj_drop = nn.Dropout(proj_drop)
+        self.rpe = RPE(patch_size, num_heads) if enable_rpe else None
+
+    def _forward_dense(self, point):
+        """non-flash branch (ptv3m1:173-206): every patch is a dense [K, K] softmax; the patch size shrinks to the smallest scene
+        so that no mask is needed"""
+        oh = point.host_offset()
+        self.patch_size = min(min(b - a for a, b in zip([0] + list(oh[:-1]), oh)), self.patch_size_max)
+        H, K, C = self.num_heads, self.patch_size, self.channels
+        pad, unpad, _ = self.get_padding_and_inverse(point)
+        order = point.serialized_order[self.order_index][pad]
+        inverse = unpad[point.serialized_inverse[self.order_index]]
+        qkv = self.qkv(point.feat)[order]
+        q, k, v = qkv.reshape(-1, K, 3, H, C // H).permute(2, 0, 3, 1, 4).unbind(0)        # each [P, H, K, D]
+        if self.upcast_attention:
+            q, k = q.float(), k.float()
+        logits = (q * self.scale) @ k.transpose(-2, -1)
+        if self.enable_rpe:
+            key = f"rel_pos_{self.order_index}"
+            if key not in point:
+                g = point.grid_coord[order].reshape(-1, K, 3)
+                point[key] = g.unsqueeze(2) - g.unsqueeze(1)
+            logits = logits + self.rpe(point[key])
+        if self.upcast_softmax:
+            logits = logits.float()
+        prob = self.attn_drop(self.softmax(logits)).to(qkv.dtype)
+        feat = (prob @ v).transpose(1, 2).reshape(-1, C)[inverse]
+        point.feat = self.proj_drop(self.proj(feat))
+        return point
 
     @torch.no_grad()
     def get_padding_and_inverse(self, point):
@@ -195,6 +253,8 @@ class SerializedAttention(PointModule):
         return point[key]
 
     def forward(self, point, proj_bias_grad_elsewhere=False):
+        if not self.enable_flash:
+            return self._forward_dense(point)
         H, K, C = self.num_heads, self.patch_size, self.channels
         _, _, cu_seqlens = self.get_padding_and_inverse(point)
         B = ops.binding()

@@ -158,3 +158,26 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "points/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_non_flash_rpe_attention_branch_matches_reference_fixture(golden_dir):
+    """SerializedAttention(enable_flash=False, enable_rpe=True) of the mirror (the reference's eager branch, ptv3m1:29-48,173-206)
+    against the reference module itself (tests/golden/attention_rpe.npz, tools/gen_golden.py): output, input gradient and the
+    gradient of the RPE table, loaded through the reference's state_dict.  Pure torch: runs on CPU."""
+    from pointcept_b200.ptv3 import SerializedAttention
+    from pointcept_b200.structure import Point
+    g = np.load(os.path.join(golden_dir, "attention_rpe.npz"))
+    attn = SerializedAttention(channels=32, num_heads=2, patch_size=64, enable_rpe=True, enable_flash=False, upcast_attention=True,
+                               upcast_softmax=True, order_index=1)
+    attn.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")})
+    feat = torch.from_numpy(g["feat"]).requires_grad_(True)
+    offset = torch.from_numpy(g["offset"])
+    pt = Point(offset=offset, offset_host=[int(v) for v in g["offset"]], grid_coord=torch.from_numpy(g["grid_coord"]), feat=feat,
+               serialized_order=torch.from_numpy(g["order"]), serialized_inverse=torch.from_numpy(g["inverse"]),
+               pad=torch.from_numpy(g["pad"]), unpad=torch.from_numpy(g["unpad"]), cu_seqlens_key=torch.from_numpy(g["cu"]))
+    out = attn(pt).feat
+    assert attn.patch_size == int(g["patch_size"]) == 48          # shrunk to the smallest scene
+    out.backward(torch.from_numpy(g["dout"]))
+    assert torch.allclose(out.detach(), torch.from_numpy(g["out"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(feat.grad, torch.from_numpy(g["dfeat"]), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(attn.rpe.rpe_table.grad, torch.from_numpy(g["d_rpe_table"]), rtol=1e-4, atol=1e-6)

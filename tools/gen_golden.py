@@ -135,6 +135,36 @@ def gen_point_and_padding():
     print("attention_dense.npz")
 
 
+def gen_attention_rpe():
+    """the reference's non-flash branch with RPE (ptv3m1:29-48,173-206) as a whole module: state_dict, inputs, tables, output, grads"""
+    ref = ref_import.load_models(use_shims=False)
+    Point, SA = ref.structure.Point, ref.ptv3.SerializedAttention
+    torch.manual_seed(11)
+    C, H = 32, 2
+    offset = [150, 150 + 48, 150 + 48 + 101]
+    N = offset[-1]
+    attn = SA(channels=C, num_heads=H, patch_size=64, enable_rpe=True, enable_flash=False, upcast_attention=True, upcast_softmax=True)
+    with torch.no_grad():
+        attn.rpe.rpe_table.normal_(0.0, 0.5)
+    rng = np.random.default_rng(5)
+    lin = rng.choice(24 * 24 * 24, size=N, replace=False)
+    gc = torch.from_numpy(np.stack([lin // 576, (lin // 24) % 24, lin % 24], 1).astype(np.int32))
+    feat = torch.randn(N, C, requires_grad=True)
+    pt = Point(offset=torch.tensor(offset), grid_coord=gc, feat=feat)
+    pt.serialization(order=("z", "hilbert"), shuffle_orders=False)
+    attn.order_index = 1
+    res = attn(pt)
+    g = torch.randn_like(res.feat)
+    res.feat.backward(g)
+    out = {f"sd::{k}": v.detach().numpy() for k, v in attn.state_dict().items()}
+    out.update(offset=np.array(offset), grid_coord=gc.numpy(), feat=feat.detach().numpy(), dout=g.numpy(), out=res.feat.detach().numpy(),
+               dfeat=feat.grad.numpy(), d_rpe_table=attn.rpe.rpe_table.grad.numpy(), patch_size=np.int64(attn.patch_size),
+               order=pt.serialized_order.numpy(), inverse=pt.serialized_inverse.numpy(),
+               pad=pt["pad"].numpy(), unpad=pt["unpad"].numpy(), cu=pt["cu_seqlens_key"].numpy())
+    np.savez_compressed(os.path.join(OUT, "attention_rpe.npz"), **out)
+    print("attention_rpe.npz patch_size", attn.patch_size)
+
+
 from oracle.ptv3_cpu import TINY_CFG  # noqa: E402
 
 
@@ -173,6 +203,10 @@ def gen_ptv3_tiny():
 
 if __name__ == "__main__" and "--only-tiny" in sys.argv:
     gen_ptv3_tiny()
+if __name__ == "__main__" and "--only-rpe" in sys.argv:
+    assert ref_import.available(), "needs /root/reference"
+    gen_attention_rpe()
+    sys.exit(0)
 
 
 if __name__ == "__main__":

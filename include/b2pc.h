@@ -261,6 +261,63 @@ int b2pc_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int64_t n, in
                          size_t workspace_bytes, b2pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * GPU voxelisation + collate: replaces the per-scene numpy GridSample transform
+ * (pointcept/datasets/transform.py:840-958: floor(coord / grid_size), fnv_hash_vec :997-1011 /
+ * ravel_hash_vec :980-995, np.argsort, np.unique(return_inverse, return_counts), per-voxel pick)
+ * for a whole batch of raw scenes at once, delivering collate_fn's layout
+ * (pointcept/datasets/utils.py:19-73: concatenated points + cumulative offset).
+ * ------------------------------------------------------------------------------------------- */
+
+/* coord [N,3] fp32 (concatenated raw scenes), offset [B] int64 cumulative raw scene sizes (device), every scene non-empty,
+ * max_scene_len = the largest scene (known on the host).  grid_size_host[3] (double).  hash_type 0 = FNV-1a 64, 1 = ravel.
+ * math_f64 != 0: coord / grid_size in float64 (NumPy >= 2 promotion of `float32 array / 0-d float64 array`); 0: in float32
+ * (NumPy 1.x value-based casting).  Outputs:
+ *   grid_coord [N,3] int64   floor(coord / grid) - per-scene minimum          (transform.py:863-866)
+ *   inverse    [N]   int64   rank of the point's voxel among the scene's voxels in ascending hash order (:888-890)
+ *   sort_index [N]   int64   idx_sort of every scene, concatenated, as global rows (:868; stable order inside a voxel)
+ *   vox_start  [N]   int64   first M entries: position in sort_index of each voxel's first member  (cumsum of count, :878)
+ *   vox_count  [N]   int64   first M entries: members per voxel (np.unique's count, :870)
+ *   meta [1 + 5B] int64: [0] = M; [1..B] = cumulative voxels per scene (the sampled batch's `offset`); [1+B..2B] = count.max()
+ *        per scene; [1+2B + 3b + j] = minimum cell of scene b (min_coord = that * grid_size, :867). */
+size_t b2pc_grid_sample_workspace_bytes(int64_t n, int batch_size, int64_t max_scene_len);
+int b2pc_grid_sample_plan(const float* coord, const int64_t* offset, int batch_size, int64_t n, int64_t max_scene_len,
+                          const double* grid_size_host, int hash_type, int math_f64, int64_t* grid_coord, int64_t* inverse,
+                          int64_t* sort_index, int64_t* vox_start, int64_t* vox_count, int64_t* meta, void* workspace,
+                          size_t workspace_bytes, b2pc_stream_t stream);
+/* idx[v] = one member row of voxel v, v < m.  mode 0 (train, transform.py:876-881): member (u % count) with u uniform in
+ * [0, count.max()) from a counter-based generator keyed by (arg = seed, v) -- the reference's distribution, modulo bias
+ * included; mode 1 (test, :914-916): member (arg % count), arg = fragment number. */
+int b2pc_grid_sample_select(const int64_t* sort_index, const int64_t* vox_start, const int64_t* vox_count, const int64_t* meta,
+                            int batch_size, int64_t m, int mode, uint64_t arg, int64_t* idx, b2pc_stream_t stream);
+/* displacement[v, :] = (coord[idx[v]] / grid - min) - grid_coord - 0.5 (transform.py:893-895); out_f64 selects the output type */
+int b2pc_grid_sample_displacement(const float* coord, const int64_t* idx, const int64_t* meta, int batch_size, int64_t m,
+                                  const double* grid_size_host, int math_f64, void* out, int out_f64, b2pc_stream_t stream);
+/* dst[i, :] = src[idx[i], :], rows of row_bytes bytes of any payload type: index_operator (transform.py:24-40) for every
+ * per-point key of the batch in the sampled order. */
+int b2pc_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t m, void* dst, b2pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Variants sharing the kernels: evaluation-time operators and PointROPE.
+ * ------------------------------------------------------------------------------------------- */
+
+/* pointops.knn_query (libs/pointops/functions/query.py:7-26, src/knn_query/knn_query_cuda_kernel.cu:60-104): for every query
+ * new_xyz[i] of scene b the nsample nearest points of xyz inside the same scene, ascending.  xyz [n,3], new_xyz [m,3] fp32,
+ * offset / new_offset [B] int32 cumulative.  idx [m,nsample] int32 (-1 = fewer than nsample points), dist2 [m,nsample] squared
+ * distances (1e10 placeholder); the Python surface returns sqrt(dist2) as the reference does.  1 <= nsample <= 128. */
+int b2pc_knn_query(const float* xyz, const int32_t* offset, const float* new_xyz, const int32_t* new_offset, int batch_size,
+                   int64_t m, int nsample, int32_t* idx, float* dist2, b2pc_stream_t stream);
+/* Fragment voting of the tester (pointcept/engines/test.py:193-203): pred[index[i], :] += softmax(logits[i, :]).
+ * logits [n, n_classes] (dtype enum), index [n] int64, pred [*, n_classes] fp32. */
+int b2pc_vote_accumulate(const void* logits, int dtype, const int64_t* index, int64_t n, int n_classes, float* pred,
+                         b2pc_stream_t stream);
+/* PointROPE (libs/pointrope/kernels.cu:19-103; litept_v1.py:29-59): in-place rotary embedding of n_heads heads of head_dim
+ * channels per token with integer positions pos [n_tokens,3] int64; fwd = +F0 forward, -F0 backward (the rotation's inverse).
+ * token_stride (elements) lets the packed qkv [T,3,H,D] be rotated in place: tokens = qkv, token_stride = 3*H*D, n_heads = 2*H
+ * rotates q and k and leaves v.  head_dim % 6 == 0. */
+int b2pc_point_rope(void* tokens, int dtype, const int64_t* pos, int64_t n_tokens, int64_t token_stride, int n_heads,
+                    int head_dim, float base, float fwd, b2pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Built-in per-entry-point timing (bench.py's roofline leg; binding independent because it lives below the C ABI).
  * While enabled, every hot entry point brackets its kernels with a CUDA-event pair on the caller's stream and records the
  * ALGORITHMIC work of the call (compulsory bytes, and flops where the host knows them).

@@ -1,7 +1,7 @@
 """pointcept_b200 -- B200 (sm_100a) operators behind Pointcept's PT-v3 / SpUNet hot path.
 
 ``install()`` registers the drop-in modules under the import names the reference uses
-(``spconv``, ``spconv.pytorch`` and optionally ``flash_attn``) so unmodified Pointcept model files
+(``spconv``, ``spconv.pytorch``, optionally ``flash_attn``, and with ``extras=True`` ``pointrope`` and ``pointops.knn_query``) so unmodified Pointcept model files
 and configs resolve to these operators.
 """
 import sys
@@ -9,7 +9,7 @@ import sys
 __version__ = "0.1.0"
 
 
-def install(flash_attn=True):
+def install(flash_attn=True, extras=False):
     from . import spconv as _spconv
     sys.modules["spconv"] = _spconv
     sys.modules["spconv.pytorch"] = _spconv.pytorch
@@ -25,3 +25,11 @@ def install(flash_attn=True):
         m.flash_attn_interface = _fa
         sys.modules["flash_attn"] = m
         sys.modules["flash_attn.flash_attn_interface"] = _fa
+    if extras:
+        import types
+        from . import pointops as _po, pointrope as _pr
+        sys.modules["pointrope"] = _pr
+        if "pointops" not in sys.modules:      # only the query the evaluation path of PT-v3 / SpUNet uses; never shadow a real pointops
+            m = types.ModuleType("pointops")
+            m.knn_query = _po.knn_query
+            sys.modules["pointops"] = m

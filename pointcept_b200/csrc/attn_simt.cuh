@@ -211,10 +211,14 @@ inline int launch_attn_fwd_simt(const void* qkv, const int32_t* cu, int n_seq, i
   dim3 grid(n_seq, (unsigned)ceil_div(max_seqlen, kAsQ), H);
 #define B2PC_AF(DD) attn_fwd_simt_kernel<T, DD><<<grid, kAsQ, 0, stream>>>((const T*)qkv, cu, t, H, scale, (T*)out, lse)
   switch (D) {
+    case 8: B2PC_AF(8); break;
     case 16: B2PC_AF(16); break;
+    case 18: B2PC_AF(18); break;   // LitePT / PT-v3m3 RoPE heads (litept_v1.py, head_dim 18)
+    case 24: B2PC_AF(24); break;
     case 32: B2PC_AF(32); break;
+    case 48: B2PC_AF(48); break;
     case 64: B2PC_AF(64); break;
-    default: set_error("patch_attn_fwd(simt): head_dim %d not in {16,32,64}", D); return B2PC_ERR_UNSUPPORTED;
+    default: set_error("patch_attn_fwd(simt): head_dim %d not in {8,16,18,24,32,48,64}", D); return B2PC_ERR_UNSUPPORTED;
   }
 #undef B2PC_AF
   count_launches(1);
@@ -239,10 +243,14 @@ inline int launch_attn_bwd_simt(const void* dout, const void* qkv, const void* o
   attn_bwd_dq_simt_kernel<T, DD><<<grid, kAsQ, 0, stream>>>((const T*)dout, (const T*)qkv, lse, delta, cu, t, H, scale, (T*)dqkv); \
   attn_bwd_dkv_simt_kernel<T, DD><<<grid, kAsQ, 0, stream>>>((const T*)dout, (const T*)qkv, lse, delta, cu, t, H, scale, (T*)dqkv)
   switch (D) {
+    case 8: B2PC_AB(8); break;
     case 16: B2PC_AB(16); break;
+    case 18: B2PC_AB(18); break;
+    case 24: B2PC_AB(24); break;
     case 32: B2PC_AB(32); break;
+    case 48: B2PC_AB(48); break;
     case 64: B2PC_AB(64); break;
-    default: set_error("patch_attn_bwd(simt): head_dim %d not in {16,32,64}", D); return B2PC_ERR_UNSUPPORTED;
+    default: set_error("patch_attn_bwd(simt): head_dim %d not in {8,16,18,24,32,48,64}", D); return B2PC_ERR_UNSUPPORTED;
   }
 #undef B2PC_AB
   count_launches(3);

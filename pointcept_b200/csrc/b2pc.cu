@@ -10,6 +10,8 @@
 #include "layernorm.cuh"
 #include "fused.cuh"
 #include "pool.cuh"
+#include "voxelize.cuh"
+#include "eval_ops.cuh"
 #ifndef B2PC_NO_UMMA
 #include "attn_umma.cuh"
 #include "spconv_umma.cuh"
@@ -449,6 +451,106 @@ int b2pc_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int64_t n, in
   B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
   B2PC_CHECK_ARG(dy && x && dx && colsum && workspace, "gelu_bwd_colsum: null pointer");
   return launch_gelu_bwd_colsum(dy, x, dtype, n, c, dx, colsum, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- GPU voxelisation / collate -----------------------------------------------------------------------------
+size_t b2pc_grid_sample_workspace_bytes(int64_t n, int batch_size, int64_t max_scene_len) {
+  if (n <= 0 || batch_size <= 0 || max_scene_len <= 0) return 256;
+  return grid_sample_workspace_bytes(n, batch_size, max_scene_len);
+}
+
+int b2pc_grid_sample_plan(const float* coord, const int64_t* offset, int batch_size, int64_t n, int64_t max_scene_len,
+                          const double* grid_size_host, int hash_type, int math_f64, int64_t* grid_coord, int64_t* inverse,
+                          int64_t* sort_index, int64_t* vox_start, int64_t* vox_count, int64_t* meta, void* workspace,
+                          size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, (double)n * (12.0 + 24.0 + 8.0 * 24.0 + 40.0));
+  B2PC_CHECK_ARG(coord && offset && grid_size_host && grid_coord && inverse && sort_index && vox_start && vox_count && meta && workspace,
+                 "grid_sample_plan: null pointer");
+  return launch_grid_sample_plan(coord, offset, batch_size, n, max_scene_len, grid_size_host, hash_type, math_f64, grid_coord, inverse,
+                                 sort_index, vox_start, vox_count, meta, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b2pc_grid_sample_select(const int64_t* sort_index, const int64_t* vox_start, const int64_t* vox_count, const int64_t* meta,
+                            int batch_size, int64_t m, int mode, uint64_t arg, int64_t* idx, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(sort_index && vox_start && vox_count && meta && idx, "grid_sample_select: null pointer");
+  B2PC_CHECK_ARG(m >= 0 && batch_size >= 1 && (mode == 0 || mode == 1), "grid_sample_select: bad arguments");
+  if (m == 0) return B2PC_OK;
+  gs_select_kernel<<<(unsigned)ceil_div(m, kGsThreads), kGsThreads, 0, (cudaStream_t)stream>>>(sort_index, vox_start, vox_count, meta,
+                                                                                             batch_size, m, mode, arg, idx);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("grid_sample_select");
+  return B2PC_OK;
+}
+
+int b2pc_grid_sample_displacement(const float* coord, const int64_t* idx, const int64_t* meta, int batch_size, int64_t m,
+                                  const double* grid_size_host, int math_f64, void* out, int out_f64, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(coord && idx && meta && grid_size_host && out, "grid_sample_displacement: null pointer");
+  B2PC_CHECK_ARG(m >= 0 && batch_size >= 1, "grid_sample_displacement: bad sizes");
+  if (m == 0) return B2PC_OK;
+  GsGrid gg;
+  for (int j = 0; j < 3; ++j) { gg.g[j] = grid_size_host[j]; gg.gf[j] = (float)grid_size_host[j]; }
+  const unsigned blocks = (unsigned)ceil_div(m, kGsThreads);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (math_f64 && out_f64) gs_displacement_kernel<true, double><<<blocks, kGsThreads, 0, s>>>(coord, idx, meta, batch_size, m, gg, (double*)out);
+  else if (math_f64) gs_displacement_kernel<true, float><<<blocks, kGsThreads, 0, s>>>(coord, idx, meta, batch_size, m, gg, (float*)out);
+  else if (out_f64) gs_displacement_kernel<false, double><<<blocks, kGsThreads, 0, s>>>(coord, idx, meta, batch_size, m, gg, (double*)out);
+  else gs_displacement_kernel<false, float><<<blocks, kGsThreads, 0, s>>>(coord, idx, meta, batch_size, m, gg, (float*)out);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("grid_sample_displacement");
+  return B2PC_OK;
+}
+
+int b2pc_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t m, void* dst, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(src && idx && dst, "gather_rows: null pointer");
+  B2PC_CHECK_ARG(row_bytes > 0 && m >= 0, "gather_rows: bad sizes");
+  if (m == 0) return B2PC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const uintptr_t al = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)row_bytes;
+  auto blocks = [&](int64_t vecs) { int64_t b = ceil_div(m * vecs, kGsThreads); return (unsigned)(b > kNumSMs * 16 ? kNumSMs * 16 : b); };
+  if (al % 16 == 0) gather_rows_kernel<uint4><<<blocks(row_bytes / 16), kGsThreads, 0, s>>>((const uint4*)src, row_bytes / 16, idx, m, (uint4*)dst);
+  else if (al % 8 == 0) gather_rows_kernel<uint2><<<blocks(row_bytes / 8), kGsThreads, 0, s>>>((const uint2*)src, row_bytes / 8, idx, m, (uint2*)dst);
+  else if (al % 4 == 0) gather_rows_kernel<uint32_t><<<blocks(row_bytes / 4), kGsThreads, 0, s>>>((const uint32_t*)src, row_bytes / 4, idx, m, (uint32_t*)dst);
+  else gather_rows_kernel<uint8_t><<<blocks(row_bytes), kGsThreads, 0, s>>>((const uint8_t*)src, row_bytes, idx, m, (uint8_t*)dst);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("gather_rows");
+  return B2PC_OK;
+}
+
+// ---- variants sharing the kernels ----------------------------------------------------------------------------
+int b2pc_knn_query(const float* xyz, const int32_t* offset, const float* new_xyz, const int32_t* new_offset, int batch_size, int64_t m,
+                   int nsample, int32_t* idx, float* dist2, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(xyz && offset && new_xyz && new_offset && idx && dist2, "knn_query: null pointer");
+  return launch_knn_query(xyz, offset, new_xyz, new_offset, batch_size, m, nsample, idx, dist2, (cudaStream_t)stream);
+}
+
+int b2pc_vote_accumulate(const void* logits, int dtype, const int64_t* index, int64_t n, int n_classes, float* pred, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(logits && index && pred, "vote_accumulate: null pointer");
+  B2PC_CHECK_ARG(n >= 0 && n_classes >= 1 && dtype >= 0 && dtype <= 2, "vote_accumulate: bad arguments");
+  if (n == 0) return B2PC_OK;
+  const unsigned blocks = (unsigned)ceil_div(n * 32, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == B2PC_F32) vote_accumulate_kernel<float><<<blocks, 256, 0, s>>>((const float*)logits, index, n, n_classes, pred);
+  else if (dtype == B2PC_F16) vote_accumulate_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)logits, index, n, n_classes, pred);
+  else vote_accumulate_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)logits, index, n, n_classes, pred);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("vote_accumulate");
+  return B2PC_OK;
+}
+
+int b2pc_point_rope(void* tokens, int dtype, const int64_t* pos, int64_t n_tokens, int64_t token_stride, int n_heads, int head_dim, float base,
+                    float fwd, b2pc_stream_t stream) {
+  B2PC_CHECK_ARG(tokens && pos, "point_rope: null pointer");
+  B2PC_CHECK_ARG(head_dim > 0 && head_dim % 6 == 0, "point_rope: token dim must be multiple of 6 (got %d)", head_dim);
+  B2PC_CHECK_ARG(n_tokens >= 0 && n_heads >= 1 && token_stride >= (int64_t)n_heads * head_dim && dtype >= 0 && dtype <= 2, "point_rope: bad arguments");
+  if (n_tokens == 0) return B2PC_OK;
+  const unsigned blocks = (unsigned)ceil_div(n_tokens * (head_dim / 2), 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == B2PC_F32) point_rope_kernel<float><<<blocks, 256, 0, s>>>((float*)tokens, pos, n_tokens, token_stride, n_heads, head_dim, base, fwd);
+  else if (dtype == B2PC_F16) point_rope_kernel<__half><<<blocks, 256, 0, s>>>((__half*)tokens, pos, n_tokens, token_stride, n_heads, head_dim, base, fwd);
+  else point_rope_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((__nv_bfloat16*)tokens, pos, n_tokens, token_stride, n_heads, head_dim, base, fwd);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("point_rope");
+  return B2PC_OK;
 }
 
 void b2pc_profile_enable(int on) {

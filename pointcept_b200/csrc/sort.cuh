@@ -151,7 +151,7 @@ inline size_t sort_workspace_bytes(int64_t n, int n_orders) {
 inline int launch_sort(const int64_t* code, int64_t n, int n_orders, int key_bits, int64_t* order, int64_t* inverse,
                        void* ws, size_t ws_bytes, cudaStream_t stream) {
   B2PC_CHECK_ARG(n >= 0 && n < (1ll << 31), "serialize_sort: n %lld out of range", (long long)n);
-  B2PC_CHECK_ARG(n_orders >= 1 && n_orders <= 8, "serialize_sort: n_orders %d outside [1,8]", n_orders);
+  B2PC_CHECK_ARG(n_orders >= 1 && n_orders <= 4096, "serialize_sort: n_orders %d outside [1,4096]", n_orders);
   B2PC_CHECK_ARG(key_bits >= 1 && key_bits <= 64, "serialize_sort: key_bits %d outside [1,64]", key_bits);
   if (ws_bytes < sort_workspace_bytes(n, n_orders)) {
     set_error("serialize_sort: workspace %zu < required %zu", ws_bytes, sort_workspace_bytes(n, n_orders));

@@ -21,7 +21,7 @@ constexpr int kCuM = 128;       // output rows per CTA (= threads)
 constexpr int kCuMaxKV = 32;    // kernel volume limit of this path (27 for 3^3, 8 for 2^3)
 constexpr int kCuMaxStages = 4;   // ring depth (prefetch distance 2)
 
-struct ConvUmmaCfg { int kc, n_tile, stages, tmem_cols, smem_bytes, idx_rows, grp, ksplit; };
+struct ConvUmmaCfg { int kc, n_tile, tmem_cols, smem_bytes, idx_rows, ksplit; };
 
 inline ConvUmmaCfg conv_umma_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   ConvUmmaCfg c;
@@ -43,18 +43,9 @@ inline ConvUmmaCfg conv_umma_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   }
   c.tmem_cols = 32;
   while (c.tmem_cols < c.n_tile) c.tmem_cols <<= 1;
-  const int unit_bytes = kCuM * c.kc * 2 + c.n_tile * c.kc * 2;
-  // narrow layers (one channel chunk per offset): several kernel offsets share one pipeline stage, i.e. one barrier,
-  // one burst of tcgen05.mma and one commit per `grp` offsets instead of per offset
-  c.grp = 1;
-  if (c.kc == c_in) {
-    static const int env_grp = [] { const char* e = getenv("B2PC_CONV_GRP"); return e ? atoi(e) : 0; }();
-    c.grp = env_grp > 0 ? env_grp : 1;   // measured on B200: grouping lowers CTAs/SM and loses (profiles/README.md)
-    if (c.grp > 8) c.grp = 8;
-  }
-  c.stages = kCuMaxStages;
+  const int unit_bytes = kCuM * c.kc * 2 + c.n_tile * c.kc * 2;   // one ring stage: A tile + B tile of one (offset, chunk) unit
   c.idx_rows = kv < kCuMaxKV ? kv : kCuMaxKV;
-  c.smem_bytes = c.idx_rows * kCuM * 4 + 256 + c.stages * c.grp * unit_bytes;
+  c.smem_bytes = c.idx_rows * kCuM * 4 + 256 + kCuMaxStages * unit_bytes;
   return c;
 }
 
@@ -65,25 +56,35 @@ inline bool spconv_umma_supported(int dtype, int c_in, int c_out) {
   return true;
 }
 
-// KC_T / NT_T: compile-time channel chunk and N tile for the common layer widths (0 = use the runtime arguments); the
-// specialisations let the compiler fold the address arithmetic of the staging loops, which otherwise dominates the issue slots.
-template <typename T, int KC_T, int NT_T>
+// KC_T / NT_T: compile-time channel chunk and N tile for the common layer widths (0 = use the runtime arguments); NCC_T: compile-time
+// number of channel chunks per offset (0 = runtime).  The specialisations fold the address arithmetic of the staging loops; the
+// ring depth is a compile-time constant and the (offset, chunk) cursor advances incrementally, so the per-iteration instruction
+// stream holds no integer division (ncu of the round-1 kernel: ~250 warp instructions per iteration, most of them index math).
+// MB: hand the staged tiles to the MMA-issuing thread through a per-stage `full` mbarrier (every thread's cp.async.mbarrier.arrive.noinc
+// fires when its copies of that stage have landed) instead of cp.async.wait_group + a block-wide barrier per iteration; only thread 0
+// waits, the other warps run ahead by up to the ring depth.
+template <typename T, int KC_T, int NT_T, int NCC_T, bool MB>
 __global__ void __launch_bounds__(kCuM)
 gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                         const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
-                        int transpose_w, int flip, T* __restrict__ out, int kc_arg, int n_tile_arg, int stages, int tmem_cols, int idx_rows,
-                        int grp, int ksplit, float* __restrict__ acc) {
+                        int transpose_w, int flip, T* __restrict__ out, int kc_arg, int n_tile_arg, int tmem_cols, int idx_rows,
+                        int ksplit, float* __restrict__ acc) {
   using namespace umma;
+  constexpr int S = kCuMaxStages;   // ring depth
+  constexpr int PD = S - 2;         // prefetch distance: a refilled stage was consumed two iterations ago, so its MMAs are (almost
+                                    // always) complete already and the stage-free wait does not serialise on the tensor pipe
   const int kc = KC_T ? KC_T : kc_arg;
   const int n_tile = NT_T ? NT_T : n_tile_arg;
+  const int n_cc = NCC_T ? NCC_T : c_in / kc;
   extern __shared__ __align__(128) uint8_t smem[];
   int32_t* idx_s = reinterpret_cast<int32_t*>(smem);                       // [idx_rows][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + idx_rows * kCuM * 4);  // [kCuMaxStages]
-  uint32_t* mask_s = reinterpret_cast<uint32_t*>(bars + kCuMaxStages);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + idx_rows * kCuM * 4);  // [S]
+  uint32_t* mask_s = reinterpret_cast<uint32_t*>(bars + S);
   uint32_t* tmem_slot = mask_s + 1;
   uint8_t* act_s = reinterpret_cast<uint8_t*>(tmem_slot + 1);   // [kCuMaxKV]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + idx_rows * kCuM * 4 + 128);   // [S] (MB only)
   uint8_t* stage0 = smem + idx_rows * kCuM * 4 + 256;
-  const int a_bytes = kCuM * kc * 2, b_bytes = n_tile * kc * 2, unit_bytes = a_bytes + b_bytes, stage_bytes = grp * unit_bytes;
+  const int a_bytes = kCuM * kc * 2, b_bytes = n_tile * kc * 2, stage_bytes = a_bytes + b_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * kCuM;
@@ -91,18 +92,45 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
 
   if (warp == 0) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   if (tid == 0) {
-    for (int s = 0; s < kCuMaxStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&bars[s], 1); if (MB) mbar_init(&full[s], kCuM); }
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_cc = c_in / kc;
   const uint32_t idesc = make_idesc(128, n_tile, UmmaFmt<T>::v, UmmaFmt<T>::v, 0, transpose_w ? 1 : 0);
-  const int PD = stages - 2;  // prefetch distance: a refilled stage was consumed two iterations ago, so its MMAs are (almost
-                              // always) complete already and the stage-free wait does not serialise on the tensor pipe
-  int gi = 0;                 // iterations issued so far (uniform); stage = gi % stages, use count = gi / stages
+  const uint32_t stage0_u32 = smem_u32(stage0);
+
+  // ---- loop-invariant staging addresses -------------------------------------------------------------------------------------
+  // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16
+  const uint32_t a_dst0 = stage0_u32 + tid * 16;
+  // B, K-major (forward): rows n (c_out side), kc contiguous channels; piece (n, p) -> p*(n_tile*16) + n*16; thread handles pieces
+  // q = tid + i*128, i.e. p = tid % ppr (fixed) and n = tid / ppr + i * (128 / ppr)
+  // B, MN-major (backward-data): rows kk (weight's c_out axis = reduction side), n_tile contiguous; piece (kk, p) -> p*(kc*16) + kk*16
+  const int ppr = transpose_w ? n_tile / 8 : kc / 8;                 // pieces per weight row
+  const int b_total = transpose_w ? kc * ppr : n_tile * ppr;         // pieces per B tile
+  const int b_r = tid / ppr, b_p = tid - b_r * ppr;
+  const int rows_per_pass = kCuM / ppr;                              // ppr <= 32 divides 128
+  const T* b_src0;
+  int64_t b_src_step;
+  uint32_t b_dst0, b_dst_step;
+  if (!transpose_w) {
+    b_src0 = weight + (int64_t)(n0 + b_r) * kv * c_in + b_p * 8;
+    b_src_step = (int64_t)rows_per_pass * kv * c_in;
+    b_dst0 = stage0_u32 + a_bytes + b_p * (n_tile * 16) + b_r * 16;
+  } else {
+    b_src0 = weight + (int64_t)b_r * kv * c_out + n0 + b_p * 8;
+    b_src_step = (int64_t)rows_per_pass * kv * c_out;
+    b_dst0 = stage0_u32 + a_bytes + b_p * (kc * 16) + b_r * 16;
+  }
+  b_dst_step = rows_per_pass * 16;
+  // UMMA descriptors of stage 0; other stages / K steps add a 16-byte-unit offset to the address field
+  const uint64_t da0 = make_smem_desc(stage0_u32, kCuM * 16, 128);
+  const uint64_t db0 = transpose_w ? make_smem_desc(stage0_u32 + a_bytes, 128, kc * 16) : make_smem_desc(stage0_u32 + a_bytes, n_tile * 16, 128);
+  const uint32_t da_ks = (2 * kCuM * 16) >> 4, db_ks = (transpose_w ? 256 : 2 * n_tile * 16) >> 4, d_stage = stage_bytes >> 4;
+
+  int gi = 0;                 // iterations issued so far (uniform); stage = gi % S, use count = gi / S
 
   // kernel offsets are processed in chunks of kCuMaxKV (the rulebook slice of a chunk lives in shared memory)
   for (int kb = 0; kb < kv; kb += kCuMaxKV) {
@@ -141,77 +169,94 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
       mask &= mine;
     }
     const int n_act = __popc(mask);
-    const int n_units = n_act * n_cc;             // unit = (active offset, channel chunk)
-    const int n_it = (n_units + grp - 1) / grp;   // an iteration (= pipeline stage) carries up to grp units
+    const int n_it = n_act * n_cc;                // iteration = unit = (active offset, channel chunk)
     if (tid < n_act) act_s[tid] = (uint8_t)__fns(mask, 0, tid + 1);   // active offsets of this chunk, in order
     __syncthreads();
 
-    auto issue_loads = [&](int it, int s) {
-     for (int u = 0; u < grp; ++u) {
-      const int unit = it * grp + u;
-      if (unit >= n_units) break;
-      uint8_t* a_s = stage0 + s * stage_bytes + u * unit_bytes;
-      uint8_t* b_s = a_s + a_bytes;
-      const int kl = act_s[unit / n_cc];              // offset inside the chunk
+    int ld_a = 0, ld_cc = 0;   // cursor of the next unit to load: index into act_s, channel chunk
+    auto issue_loads = [&](int s) {
+      const int kl = act_s[ld_a];                     // offset inside the chunk
       const int k = kb + kl;                          // weight slice
-      const int c0 = (unit % n_cc) * kc;
-      // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16
+      const int c0 = ld_cc * kc;
+      const uint32_t s_off = s * stage_bytes;
       const int32_t src = idx_s[kl * kCuM + tid];
       const T* g = feat + (int64_t)(src >= 0 ? src : 0) * c_in + c0;
-      const uint32_t a_dst = smem_u32(a_s) + tid * 16;
-      for (int p = 0; p < kc / 8; ++p) cp_async16(a_dst + p * (kCuM * 16), g + p * 8, src >= 0);
-      if (!transpose_w) {
-        // B K-major: rows n (c_out side), kc contiguous channels; piece (n, p) -> p*(n_tile*16) + n*16
-        const int ppr = kc / 8;
-        for (int q = tid; q < n_tile * ppr; q += kCuM) {
-          const int n = q / ppr, p = q % ppr;
-          cp_async16(smem_u32(b_s) + p * (n_tile * 16) + n * 16, weight + ((int64_t)(n0 + n) * kv + k) * c_in + c0 + p * 8, true);
+      const uint32_t a_dst = a_dst0 + s_off;
+#pragma unroll
+      for (int p = 0; p < (KC_T ? KC_T / 8 : 8); ++p)
+        if (KC_T || p < kc / 8) cp_async16(a_dst + p * (kCuM * 16), g + p * 8, src >= 0);
+      const T* bs = b_src0 + (transpose_w ? ((int64_t)c0 * kv + k) * c_out : (int64_t)k * c_in + c0);
+      uint32_t bd = b_dst0 + s_off;
+      if (KC_T && NT_T) {
+        constexpr int kPieces = (KC_T ? KC_T : 8) * (NT_T ? NT_T : 8) / 8;     // same count for both operand majors
+        if (kPieces >= kCuM) {
+#pragma unroll
+          for (int i = 0; i < kPieces / kCuM; ++i) { cp_async16(bd, bs, true); bs += b_src_step; bd += b_dst_step; }
+        } else if (tid < kPieces) {
+          cp_async16(bd, bs, true);
         }
-      } else {
-        // B MN-major: rows kk (reduction side = weight's c_out axis), n_tile contiguous; piece (kk, p) -> p*(kc*16) + kk*16
-        const int ppr = n_tile / 8;
-        for (int q = tid; q < kc * ppr; q += kCuM) {
-          const int kk = q / ppr, p = q % ppr;
-          cp_async16(smem_u32(b_s) + p * (kc * 16) + kk * 16, weight + ((int64_t)(c0 + kk) * kv + k) * c_out + n0 + p * 8, true);
+      } else {   // runtime tile shape (ppr need not divide 128): per-piece index arithmetic
+        const T* wk = weight + (transpose_w ? ((int64_t)c0 * kv + k) * c_out + n0 : ((int64_t)n0 * kv + k) * c_in + c0);
+        const int64_t row_stride = (int64_t)kv * (transpose_w ? c_out : c_in);
+        const uint32_t plane = (transpose_w ? kc : n_tile) * 16;
+        for (int q = tid; q < b_total; q += kCuM) {
+          const int r = q / ppr, pp = q - r * ppr;
+          cp_async16(stage0_u32 + a_bytes + s_off + pp * plane + r * 16, wk + r * row_stride + pp * 8, true);
         }
       }
-     }
+      if (++ld_cc == n_cc) { ld_cc = 0; ++ld_a; }
     };
-    auto stage_free = [&](int g) {   // stage g % stages was last read by the MMAs of global iteration g - stages
-      if (g >= stages) mbar_wait(&bars[g % stages], ((g / stages) - 1) & 1);
+    auto stage_free = [&](int g) {   // stage g % S was last read by the MMAs of global iteration g - S
+      if (g >= S) mbar_wait(&bars[g & (S - 1)], ((g / S) - 1) & 1);
     };
 
-    for (int it = 0; it < PD; ++it) {
-      if (it < n_it) { stage_free(gi + it); issue_loads(it, (gi + it) % stages); }
-      cp_async_commit();
-    }
-    for (int it = 0; it < n_it; ++it) {
-      const int nx = it + PD;
-      if (nx < n_it) { stage_free(gi + nx); issue_loads(nx, (gi + nx) % stages); }
-      cp_async_commit();
-      cp_async_wait<2>();   // groups committed: PD + it + 1; iteration `it` is group #it -> PD = 2 may stay pending
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const int s = (gi + it) % stages;
-        for (int u = 0; u < grp && it * grp + u < n_units; ++u) {
-          const uint32_t a_addr = smem_u32(stage0 + s * stage_bytes + u * unit_bytes), b_addr = a_addr + a_bytes;
-          for (int ks = 0; ks < kc / 16; ++ks) {
-            const uint64_t da = make_smem_desc(a_addr + 2 * ks * (kCuM * 16), kCuM * 16, 128);
-            const uint64_t db = transpose_w ? make_smem_desc(b_addr + ks * 256, 128, kc * 16)
-                                            : make_smem_desc(b_addr + 2 * ks * (n_tile * 16), n_tile * 16, 128);
-            mma_ss(tmem_base, da, db, idesc, (gi + it > 0 || u > 0 || ks > 0) ? 1u : 0u);
-          }
+    auto issue_mma = [&](int g) {
+      tc_fence_after();
+      const int s = g & (S - 1);
+      const uint64_t da = da0 + (uint64_t)(s * d_stage), db = db0 + (uint64_t)(s * d_stage);
+#pragma unroll
+      for (int ks = 0; ks < (KC_T ? KC_T / 16 : 4); ++ks)
+        if (KC_T || ks < kc / 16) mma_ss(tmem_base, da + ks * da_ks, db + ks * db_ks, idesc, (g > 0 || ks > 0) ? 1u : 0u);
+      mma_commit(&bars[s]);
+    };
+    if (MB) {
+#pragma unroll
+      for (int it = 0; it < PD; ++it)
+        if (it < n_it) { stage_free(gi + it); issue_loads((gi + it) & (S - 1)); cp_async_mbar_arrive_noinc(&full[(gi + it) & (S - 1)]); }
+      for (int it = 0; it < n_it; ++it) {
+        if (it + PD < n_it) {
+          const int g2 = gi + it + PD;
+          stage_free(g2);
+          issue_loads(g2 & (S - 1));
+          cp_async_mbar_arrive_noinc(&full[g2 & (S - 1)]);
         }
-        mma_commit(&bars[s]);
+        if (tid == 0) {
+          const int g = gi + it;
+          mbar_wait(&full[g & (S - 1)], (g / S) & 1);
+          fence_proxy_async();
+          issue_mma(g);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < PD; ++it) {
+        if (it < n_it) { stage_free(gi + it); issue_loads((gi + it) & (S - 1)); }
+        cp_async_commit();
+      }
+      for (int it = 0; it < n_it; ++it) {
+        if (it + PD < n_it) { stage_free(gi + it + PD); issue_loads((gi + it + PD) & (S - 1)); }
+        cp_async_commit();
+        cp_async_wait<PD>();   // groups committed: PD + it + 1; iteration `it` is group #it -> PD may stay pending
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) issue_mma(gi + it);
       }
     }
     gi += n_it;
     cp_async_wait<0>();
   }
   const int n_it = gi;
-  if (gi > 0) mbar_wait(&bars[(gi - 1) % stages], ((gi - 1) / stages) & 1);
+  if (gi > 0) mbar_wait(&bars[(gi - 1) & (S - 1)], ((gi - 1) / S) & 1);
   tc_fence_after();
   // epilogue: thread = row, 16 columns at a time
   const int64_t j = row0 + tid;
@@ -279,24 +324,27 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
   dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile, c.ksplit);
   float* acc = (float*)ws;
   if (c.ksplit > 1) cudaMemsetAsync(acc, 0, (size_t)n_out * c_out * sizeof(float), stream);
-#define B2PC_CONV_LAUNCH(KC, NT)                                                                                                   \
+#define B2PC_CONV_LAUNCH_(KC, NT, NCC, MB)                                                                                           \
   do {                                                                                                                             \
-    static int max_smem_set = 0;                                                                                                   \
-    if (c.smem_bytes > max_smem_set) {                                                                                             \
-      cudaFuncSetAttribute(gather_gemm_umma_kernel<T, KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);         \
-      max_smem_set = c.smem_bytes;                                                                                                 \
-    }                                                                                                                              \
-    gather_gemm_umma_kernel<T, KC, NT><<<grid, kCuM, c.smem_bytes, stream>>>(                                                      \
+    cudaFuncSetAttribute(gather_gemm_umma_kernel<T, KC, NT, NCC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);      \
+    gather_gemm_umma_kernel<T, KC, NT, NCC, MB><<<grid, kCuM, c.smem_bytes, stream>>>(                                                 \
         (const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,   \
-        c.kc, c.n_tile, c.stages, c.tmem_cols, c.idx_rows, c.grp, c.ksplit, acc);                                                  \
+        c.kc, c.n_tile, c.tmem_cols, c.idx_rows, c.ksplit, acc);                                                                   \
   } while (0)
-  if (c.kc == 32 && c.n_tile == 32) B2PC_CONV_LAUNCH(32, 32);
-  else if (c.kc == 64 && c.n_tile == 64) B2PC_CONV_LAUNCH(64, 64);
-  else if (c.kc == 64 && c.n_tile == 128) B2PC_CONV_LAUNCH(64, 128);
-  else if (c.kc == 64 && c.n_tile == 256) B2PC_CONV_LAUNCH(64, 256);
-  else if (c.kc == 16 && c.n_tile == 32) B2PC_CONV_LAUNCH(16, 32);
-  else B2PC_CONV_LAUNCH(0, 0);
+  static const bool conv_mb = [] { const char* e = getenv("B2PC_CONV_MB"); return e ? atoi(e) != 0 : false; }();   // measured on B200: the block barrier wins (profiles/README.md)
+#define B2PC_CONV_LAUNCH(KC, NT, NCC) do { if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false); } while (0)
+  const int ncc = c_in / c.kc;
+  if (c.kc == 32 && c.n_tile == 32 && ncc == 1) B2PC_CONV_LAUNCH(32, 32, 1);
+  else if (c.kc == 64 && c.n_tile == 64 && ncc == 1) B2PC_CONV_LAUNCH(64, 64, 1);
+  else if (c.kc == 64 && c.n_tile == 128 && ncc == 2) B2PC_CONV_LAUNCH(64, 128, 2);
+  else if (c.kc == 64 && c.n_tile == 256 && ncc == 4) B2PC_CONV_LAUNCH(64, 256, 4);
+  else if (c.kc == 64 && c.n_tile == 64) B2PC_CONV_LAUNCH(64, 64, 0);
+  else if (c.kc == 64 && c.n_tile == 128) B2PC_CONV_LAUNCH(64, 128, 0);
+  else if (c.kc == 64 && c.n_tile == 256) B2PC_CONV_LAUNCH(64, 256, 0);
+  else if (c.kc == 16 && c.n_tile == 32 && ncc == 1) B2PC_CONV_LAUNCH(16, 32, 1);
+  else B2PC_CONV_LAUNCH(0, 0, 0);
 #undef B2PC_CONV_LAUNCH
+#undef B2PC_CONV_LAUNCH_
   if (c.ksplit > 1) {
     int64_t fb = ceil_div(n_out * c_out / 4, 256);
     if (fb > kNumSMs * 8) fb = kNumSMs * 8;
@@ -531,11 +579,7 @@ template <typename T>
 inline int launch_bwd_weight_umma_t(const void* feat, const void* dout, const int32_t* pair, int64_t pair_stride, int64_t n_out,
                                     int c_in, int c_out, int kv, float* dweight, void* ws, cudaStream_t stream) {
   const WgradCfg c = wgrad_cfg(n_out, c_in, c_out, kv);
-  static int max_smem_set = 0;
-  if (c.smem_bytes > max_smem_set) {
-    cudaFuncSetAttribute(bwd_weight_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);
-    max_smem_set = c.smem_bytes;
-  }
+  cudaFuncSetAttribute(bwd_weight_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);   // per device, so per launch
   dim3 grid(c.n_groups * c.n_mtiles * c.n_ntiles, c.n_splits);
   bwd_weight_umma_kernel<T><<<grid, 128, c.smem_bytes, stream>>>((const T*)feat, (const T*)dout, pair, pair_stride, n_out, c_in, c_out,
                                                                  kv, (float*)ws, c);

@@ -691,3 +691,162 @@ def drop_path_add(shortcut, x, drop_prob, training):
     if keep > 0.0:
         mask.div_(keep)
     return shortcut + x * mask
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU voxelisation / collate (pointcept/datasets/transform.py:840-958, datasets/utils.py:19-73)
+# ------------------------------------------------------------------------------------------------
+class GridSamplePlan:
+    """Device-side result of b2pc_grid_sample_plan for a batch of raw scenes (see include/b2pc.h)."""
+    __slots__ = ("coord", "offset", "offset_host", "grid_size", "math_f64", "grid_coord", "inverse", "sort_index", "vox_start",
+                 "vox_count", "meta", "m", "new_offset_host", "count_max_host", "min_cell_host")
+
+    def select(self, mode, arg):
+        """idx [M] int64: one member of every voxel; mode "train" (arg = seed) or "test" (arg = fragment number)."""
+        idx = torch.empty(self.m, dtype=torch.int64, device=self.coord.device)
+        if self.m:
+            _lib.check(_lib.lib().b2pc_grid_sample_select(_p(self.sort_index), _p(self.vox_start), _p(self.vox_count), _p(self.meta),
+                                                          len(self.offset_host), self.m, 0 if mode == "train" else 1,
+                                                          ctypes.c_uint64(int(arg) & 0xFFFFFFFFFFFFFFFF), _p(idx), _stream()), "grid_sample_select")
+        return idx
+
+    def displacement(self, idx, out_dtype=None):
+        out_dtype = out_dtype or torch.float64      # numpy promotes `scaled - grid_coord(int64) - 0.5` to float64 in either mode
+        out = torch.empty((idx.shape[0], 3), dtype=out_dtype, device=idx.device)
+        g = (ctypes.c_double * 3)(*self.grid_size)
+        if idx.shape[0]:
+            _lib.check(_lib.lib().b2pc_grid_sample_displacement(_p(self.coord), _p(idx), _p(self.meta), len(self.offset_host), idx.shape[0], g,
+                                                                int(self.math_f64), _p(out), int(out_dtype == torch.float64), _stream()),
+                       "grid_sample_displacement")
+        return out
+
+
+@torch.no_grad()
+def grid_sample_plan(coord, offset_host, grid_size, hash_type="fnv", math="float64"):
+    """Voxelise B concatenated raw scenes in one pass.  coord [N,3] fp32 CUDA, offset_host: cumulative scene sizes (python ints),
+    grid_size scalar or 3 values.  One host read (voxel counts) at the end -- the only synchronisation."""
+    _need_cuda(coord)
+    coord = coord if (coord.dtype == torch.float32 and coord.is_contiguous()) else coord.float().contiguous()
+    offset_host = [int(x) for x in offset_host]
+    n, nb = coord.shape[0], len(offset_host)
+    sizes = [offset_host[0]] + [offset_host[i] - offset_host[i - 1] for i in range(1, nb)]
+    if nb == 0 or offset_host[-1] != n or min(sizes) <= 0:
+        raise ValueError("grid_sample_plan: offset must be the cumulative sizes of non-empty scenes and end at len(coord)")
+    gs = [float(grid_size)] * 3 if not hasattr(grid_size, "__len__") else [float(x) for x in grid_size]
+    assert len(gs) == 3 and hash_type in ("fnv", "ravel") and math in ("float64", "float32")
+    dev = coord.device
+    plan = GridSamplePlan()
+    plan.coord, plan.offset_host, plan.grid_size, plan.math_f64 = coord, offset_host, gs, math == "float64"
+    plan.offset = torch.tensor(offset_host, dtype=torch.int64).to(dev, non_blocking=True)
+    plan.grid_coord = torch.empty((n, 3), dtype=torch.int64, device=dev)
+    plan.inverse = torch.empty(n, dtype=torch.int64, device=dev)
+    plan.sort_index = torch.empty(n, dtype=torch.int64, device=dev)
+    plan.vox_start = torch.empty(n, dtype=torch.int64, device=dev)
+    plan.vox_count = torch.empty(n, dtype=torch.int64, device=dev)
+    plan.meta = torch.empty(1 + 5 * nb, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    row = max(sizes)
+    ws = _ws(L.b2pc_grid_sample_workspace_bytes(n, nb, row), dev)
+    g = (ctypes.c_double * 3)(*gs)
+    _lib.check(L.b2pc_grid_sample_plan(_p(coord), _p(plan.offset), nb, n, row, g, 0 if hash_type == "fnv" else 1, int(plan.math_f64),
+                                       _p(plan.grid_coord), _p(plan.inverse), _p(plan.sort_index), _p(plan.vox_start), _p(plan.vox_count),
+                                       _p(plan.meta), _p(ws), ws.numel(), _stream()), "grid_sample_plan")
+    meta = plan.meta.tolist()   # the one host read
+    plan.m = meta[0]
+    plan.new_offset_host = meta[1:1 + nb]
+    plan.count_max_host = meta[1 + nb:1 + 2 * nb]
+    plan.min_cell_host = [meta[1 + 2 * nb + 3 * b:1 + 2 * nb + 3 * b + 3] for b in range(nb)]
+    plan.vox_start, plan.vox_count = plan.vox_start[:plan.m], plan.vox_count[:plan.m]
+    return plan
+
+
+@torch.no_grad()
+def gather_rows(src, idx):
+    """src[idx] for a row-major tensor of any dtype (index_operator, transform.py:24-40)."""
+    _need_cuda(src, idx)
+    src = src.contiguous()
+    idx = idx if (idx.dtype == torch.int64 and idx.is_contiguous()) else idx.long().contiguous()
+    out = torch.empty((idx.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    row_bytes = src.element_size() * (src[0].numel() if src.shape[0] else 1)
+    if idx.shape[0] and row_bytes:
+        _lib.check(_lib.lib().b2pc_gather_rows(_p(src), row_bytes, _p(idx), idx.shape[0], _p(out), _stream()), "gather_rows")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# variants sharing the kernels (SURVEY 8(f).4): kNN query, fragment voting, PointROPE
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def knn_query(nsample, xyz, offset, new_xyz=None, new_offset=None):
+    """pointops.knn_query (libs/pointops/functions/query.py:7-26): -> idx [m,nsample] int32 (-1 placeholder), dist [m,nsample]."""
+    if new_xyz is None or new_offset is None:
+        new_xyz, new_offset = xyz, offset
+    _need_cuda(xyz, new_xyz, offset, new_offset)
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and xyz.dtype == torch.float32 and new_xyz.dtype == torch.float32
+    offset, new_offset = offset.int().contiguous(), new_offset.int().contiguous()
+    m = new_xyz.shape[0]
+    idx = torch.empty((m, nsample), dtype=torch.int32, device=xyz.device)
+    dist2 = torch.empty((m, nsample), dtype=torch.float32, device=xyz.device)
+    _lib.check(_lib.lib().b2pc_knn_query(_p(xyz), _p(offset), _p(new_xyz), _p(new_offset), offset.shape[0], m, int(nsample), _p(idx), _p(dist2),
+                                         _stream()), "knn_query")
+    return idx, torch.sqrt(dist2)
+
+
+@torch.no_grad()
+def vote_accumulate(pred, index, logits):
+    """pred[index] += softmax(logits, -1) in place (pointcept/engines/test.py:193-203); pred fp32 [N, C]."""
+    _need_cuda(pred, index, logits)
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and logits.shape[1] == pred.shape[1]
+    logits = logits.contiguous()
+    index = index if (index.dtype == torch.int64 and index.is_contiguous()) else index.long().contiguous()
+    _lib.check(_lib.lib().b2pc_vote_accumulate(_p(logits), _DTYPES[logits.dtype], _p(index), logits.shape[0], logits.shape[1], _p(pred), _stream()),
+               "vote_accumulate")
+    return pred
+
+
+def _point_rope_(tokens, pos, n_tokens, token_stride, n_heads, head_dim, base, fwd):
+    _lib.check(_lib.lib().b2pc_point_rope(_p(tokens), _DTYPES[tokens.dtype], _p(pos), n_tokens, token_stride, n_heads, head_dim, float(base),
+                                          float(fwd), _stream()), "point_rope")
+
+
+def pointrope_(tokens, positions, base, fwd):
+    """The ``pointrope.pointrope(tokens, positions, base, F0)`` entry point (libs/pointrope/pointrope.cpp): tokens [B,N,H,D] rotated IN
+    PLACE, positions [B,N,3] int64."""
+    _need_cuda(tokens, positions)
+    assert tokens.dim() == 4 and tokens.is_contiguous(), "tokens are not contiguous"
+    b, n, h, d = tokens.shape
+    assert positions.is_contiguous() and tuple(positions.shape) == (b, n, 3), "bad pos.shape"
+    assert d % 6 == 0, "token dim must be multiple of 6"
+    positions = positions if positions.dtype == torch.int64 else positions.long()
+    _point_rope_(tokens, positions, b * n, h * d, h, d, base, fwd)
+    return tokens
+
+
+class _RopeQKV(torch.autograd.Function):
+    """LitePT's q/k rotation (litept_v1.py:231-250) fused on the packed tensor: qkv [T,3,H,D] -> same layout with q and k rotated;
+    replaces two float casts, four transposes, two rope launches, a stack and a cast.  Backward = rotation by the negative angle."""
+
+    @staticmethod
+    def forward(ctx, qkv, pos, base, f0):
+        out = qkv.clone()
+        t, _, h, d = out.shape
+        _point_rope_(out, pos, t, 3 * h * d, 2 * h, d, base, f0)
+        ctx.save_for_backward(pos)
+        ctx.base, ctx.f0 = base, f0
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.clone().contiguous()
+        t, _, h, d = g.shape
+        _point_rope_(g, ctx.saved_tensors[0], t, 3 * h * d, 2 * h, d, ctx.base, -ctx.f0)
+        return g, None, None, None
+
+
+def rope_qkv(qkv, pos, base=100.0, f0=1.0):
+    _need_cuda(qkv, pos)
+    assert qkv.dim() == 4 and qkv.shape[1] == 3 and qkv.is_contiguous() and qkv.shape[3] % 6 == 0
+    pos = pos.reshape(-1, 3)
+    pos = pos if (pos.dtype == torch.int64 and pos.is_contiguous()) else pos.long().contiguous()
+    assert pos.shape[0] == qkv.shape[0]
+    return _RopeQKV.apply(qkv, pos, float(base), float(f0))

@@ -77,3 +77,37 @@ def test_dense_attention_matches_reference_branch(golden_dir):
     core.backward(torch.from_numpy(g["d_core_out"]))
     d_full = torch.zeros_like(qkv_full).index_add_(0, order, qkv.grad.reshape(-1, 3 * C))
     assert torch.allclose(d_full, torch.from_numpy(g["d_qkv_full"]), atol=2e-6, rtol=1e-4)
+
+
+# ---- GridSample (pointcept/datasets/transform.py:840-958) -----------------------------------------------------------------
+def test_grid_sample_oracle_matches_reference_fixture(golden_dir):
+    from oracle import grid_sample as ogs
+    g = np.load(os.path.join(golden_dir, "grid_sample.npz"))
+    assert np.array_equal(ogs.fnv_hash_vec(np.arange(30, dtype=np.int64).reshape(10, 3)), g["fnv_of_arange"])
+    for hash_type in ("fnv", "ravel"):
+        for gs in (0.05, 0.02):
+            for i in range(2):
+                tag = f"{hash_type}_{gs}_{i}"
+                p = ogs.plan(g[f"coord{i}"], gs, hash_type, "float64")
+                assert np.array_equal(p["inverse"], g[tag + "_inverse"]), tag
+                assert int(p["count"].max()) == int(g[tag + "_n_fragments"]), tag
+                assert np.array_equal(p["grid_coord"][ogs.select(p, 0)], g[tag + "_grid_coord"]), tag
+                assert np.array_equal((p["min_cell"] * np.float64(gs)).reshape(1, 3), g[tag + "_min_coord"]), tag
+                # whichever member the reference's (unstable) argsort put first, it lies in the voxel the oracle assigns
+                for key in ("_index0", "_last_index"):
+                    assert np.array_equal(p["inverse"][g[tag + key]], np.arange(len(p["count"]))), tag
+                if hash_type == "fnv":
+                    disp = (p["scaled"] - p["grid_coord"] - 0.5)[g[tag + "_index0"]]
+                    assert np.array_equal(disp, g[tag + "_displacement0"]), tag
+
+
+# ---- PointROPE (pointcept/models/litept/litept_v1.py:66-125) -------------------------------------------------------------
+def test_point_rope_oracle_matches_reference_fixture(golden_dir):
+    from oracle import eval_ops as oev
+    g = np.load(os.path.join(golden_dir, "point_rope.npz"))
+    for name in ("d18", "d48"):
+        y = oev.point_rope(torch.from_numpy(g[name + "_tokens"]), torch.from_numpy(g[name + "_pos"]), float(g[name + "_base"]))
+        assert float((y - torch.from_numpy(g[name + "_out"])).abs().max()) <= 1e-6, name
+        # rotation by the negative angle is the inverse (what PointROPE_func.backward applies, litept_v1.py:40-46)
+        back = oev.point_rope(y, torch.from_numpy(g[name + "_pos"]), float(g[name + "_base"]), -1.0)
+        assert float((back - torch.from_numpy(g[name + "_tokens"])).abs().max()) <= 1e-5

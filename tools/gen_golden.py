@@ -201,6 +201,71 @@ def gen_ptv3_tiny():
     print("ptv3_tiny.npz", out.feat.shape, float(out.feat.abs().mean()))
 
 
+
+def gen_grid_sample():
+    """GridSample (pointcept/datasets/transform.py:840-958) run by the reference's own class on two raw synthetic scenes:
+    everything the reference determines (hash keys, grid_coord of the sampled voxels in output order, inverse, counts, min_coord,
+    fragment count, and its displacement at its own picks) for fnv / ravel hashes and two grid sizes."""
+    t = ref_import.load_transform()
+    rng = np.random.default_rng(7)
+    scenes = []
+    for n, ext in ((9000, (1.6, 1.2, 1.0)), (5001, (0.8, 2.0, 0.5))):
+        # points on a few planes with jitter, centred so that negative coordinates occur (floor of negatives matters)
+        c = rng.random((n, 3)) * np.asarray(ext) - np.asarray(ext) / 2
+        wall = rng.integers(0, 3, n)
+        c[np.arange(n), wall] = np.round(c[np.arange(n), wall]) + rng.normal(0, 0.004, n)
+        scenes.append(c.astype(np.float32))
+    out = {f"coord{i}": c for i, c in enumerate(scenes)}
+    out["fnv_of_arange"] = t.GridSample.fnv_hash_vec(np.arange(30, dtype=np.int64).reshape(10, 3))
+    for hash_type in ("fnv", "ravel"):
+        for gs in (0.05, 0.02):
+            for i, c in enumerate(scenes):
+                tr = t.GridSample(grid_size=gs, hash_type=hash_type, mode="test", return_inverse=True, return_grid_coord=True,
+                                  return_min_coord=True, return_displacement=True)
+                parts = tr(dict(coord=c.copy(), index_valid_keys=["coord"]))
+                tag = f"{hash_type}_{gs}_{i}"
+                out[tag + "_inverse"] = parts[0]["inverse"]
+                out[tag + "_grid_coord"] = parts[0]["grid_coord"]
+                out[tag + "_min_coord"] = parts[0]["min_coord"]
+                out[tag + "_n_fragments"] = np.int64(len(parts))
+                out[tag + "_index0"] = parts[0]["index"]
+                if hash_type == "fnv":
+                    out[tag + "_displacement0"] = parts[0]["displacement"]
+                out[tag + "_last_index"] = parts[-1]["index"]
+    np.savez_compressed(os.path.join(OUT, "grid_sample.npz"), **out)
+    print("grid_sample.npz", {k: v.shape for k, v in out.items() if k.endswith("_grid_coord")})
+
+
+if __name__ == "__main__" and "--only-grid-sample" in sys.argv:
+    assert ref_import.available(), "needs /root/reference"
+    gen_grid_sample()
+    sys.exit(0)
+
+
+def gen_point_rope():
+    """PointROPE by the reference's own pure-PyTorch class (litept_v1.py:66-125): LitePT's head_dim 18 and a wider head."""
+    lp = ref_import.load_litept()
+    gen = torch.Generator().manual_seed(11)
+    out = {}
+    for name, (n, h, d, base) in {"d18": (777, 4, 18, 100.0), "d48": (300, 2, 48, 50.0)}.items():
+        tokens = torch.randn(1, h, n, d, generator=gen)
+        pos = torch.randint(0, 700, (1, n, 3), generator=gen)
+        rope = lp.PointROPE(freq=base)
+        assert hasattr(rope, "apply_rope1d"), "expected the pure-PyTorch fallback class"
+        y = rope(tokens, pos)
+        out[name + "_tokens"] = tokens[0].transpose(0, 1).contiguous().numpy()      # [N, H, D]
+        out[name + "_pos"] = pos[0].numpy()
+        out[name + "_out"] = y[0].transpose(0, 1).contiguous().numpy()
+        out[name + "_base"] = np.float32(base)
+    np.savez_compressed(os.path.join(OUT, "point_rope.npz"), **out)
+    print("point_rope.npz", {k: v.shape for k, v in out.items() if k.endswith("_out")})
+
+
+if __name__ == "__main__" and "--only-rope" in sys.argv:
+    assert ref_import.available(), "needs /root/reference"
+    gen_point_rope()
+    sys.exit(0)
+
 if __name__ == "__main__" and "--only-tiny" in sys.argv:
     gen_ptv3_tiny()
 if __name__ == "__main__" and "--only-rpe" in sys.argv:
@@ -215,5 +280,7 @@ if __name__ == "__main__":
     if "--only-tiny" not in sys.argv:
         gen_serialization()
         gen_point_and_padding()
+        gen_grid_sample()
+        gen_point_rope()
         gen_ptv3_tiny()
 

@@ -193,3 +193,40 @@ def load_models(use_shims=False):
     spunet = _load("pointcept.models.sparse_unet.spconv_unet_v1m1_base",
                    "pointcept/models/sparse_unet/spconv_unet_v1m1_base.py")
     return types.SimpleNamespace(structure=structure, modules=modules, ptv3=ptv3, spunet=spunet, misc=misc)
+
+
+def load_transform():
+    """-> the reference's pointcept/datasets/transform.py (GridSample, index_operator ...) under a private package name, with
+    only its Registry dependency loaded from the reference tree."""
+    pkg = "_ref_datasets"
+    if pkg + ".transform" in sys.modules:
+        return sys.modules[pkg + ".transform"]
+    saved = {k: sys.modules.get(k) for k in ("pointcept", "pointcept.utils", "pointcept.utils.misc", "pointcept.utils.registry")}
+    try:
+        p = _mod("pointcept")
+        p.__path__ = [os.path.join(REF, "pointcept")]
+        u = _mod("pointcept.utils")
+        u.__path__ = [os.path.join(REF, "pointcept/utils")]
+        _load("pointcept.utils.misc", "pointcept/utils/misc.py")
+        _load("pointcept.utils.registry", "pointcept/utils/registry.py")
+        return _load(pkg + ".transform", "pointcept/datasets/transform.py")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def load_litept():
+    """-> the reference's pointcept/models/litept/litept_v1.py.  ``pointrope`` (its CUDA extension) is not importable here, so the
+    module defines its pure-PyTorch PointROPE fallback (litept_v1.py:66-125) -- the CPU reference for the rotary embedding."""
+    load_models(use_shims=False)
+    sys.modules.pop("pointrope", None)
+    if "pointcept.models.litept" not in sys.modules:
+        m = _mod("pointcept.models.litept")
+        m.__path__ = []
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return _load("pointcept.models.litept.litept_v1", "pointcept/models/litept/litept_v1.py")

@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--gpu-reference-steps", type=int, default=5)
     ap.add_argument("--bucket-mb", type=int, default=100, help="DDP gradient bucket size")
     ap.add_argument("--no-static-graph", action="store_true", help="DDP without static_graph")
+    ap.add_argument("--torch-profile", default=None, help="write a torch.profiler (CUPTI) per-kernel breakdown of two extra steps to this file")
     ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of pointcept_b200.optim.FusedAdamW")
     return ap.parse_args()
 
@@ -361,6 +362,20 @@ def measure(args, workload, scenes, voxels, steps, warmup, kind="indoor", want_p
             res["profile"] = _lib.profile_collect()
             res["profile_ms_total"] = p0.elapsed_time(p1)
             res["profile_steps"] = n_prof
+        if want_profile and args.torch_profile and rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as tp:
+                run_steps(2, resident_inputs)
+                torch.cuda.synchronize()
+            rows = sorted([e for e in tp.key_averages() if e.device_time_total > 0], key=lambda e: -e.device_time_total)
+            tot = sum(e.device_time_total for e in rows)
+            with open(args.torch_profile, "w") as f:
+                f.write(f"# torch.profiler (CUPTI) device time of {workload} training steps, per step: {tot / 2e3:.2f} ms in "
+                        f"{sum(e.count for e in rows) // 2} kernels / memsets / copies\n")
+                own = sum(e.device_time_total for e in rows if "b2pc::" in e.key)
+                f.write(f"# b2pc:: kernels {100 * own / tot:.1f} % of device time\n")
+                for e in rows[:90]:
+                    f.write(f"{e.device_time_total / 2e3:9.3f} ms {100 * e.device_time_total / tot:5.1f}%  n={e.count // 2:5d}  {e.key[:150]}\n")
         # ---- timed region 2: end to end through the public API with HOST buffers ---------------------------------
         if want_e2e:
             loss_pinned = torch.zeros(steps, dtype=torch.float32).pin_memory()
@@ -411,6 +426,46 @@ def rooflines(prof, prof_ms_total, pk):
     return out, shares
 
 
+def measure_grid_sample(scenes, voxels, dev, pk, iters=20):
+    """GPU voxelisation + collate of `scenes` raw ScanNet-scale scenes (~2 raw points per 2 cm voxel): the
+    transform in front of the hot path, timed alone with CUDA events; raw points/s and its HBM roofline fraction."""
+    import numpy as np
+    import torch
+    from pointcept_b200 import datasets, synth
+    hb = synth.make_batch(scenes, seed=7, target_voxels=voxels)
+    rng = np.random.default_rng(7)
+    grid, off = hb["grid_coord"], hb["offset"]
+    raw, sizes, s = [], [], 0
+    for e in off:
+        g = grid[s:e]
+        pick = rng.integers(0, len(g), 2 * len(g))
+        raw.append(((g[pick] + rng.random((len(pick), 3))) * 0.02).astype(np.float32))
+        sizes.append(len(pick))
+        s = e
+    coord = torch.from_numpy(np.concatenate(raw)).to(dev)
+    feat = torch.randn(coord.shape[0], 6, device=dev)
+    seg = torch.randint(0, 20, (coord.shape[0],), device=dev, dtype=torch.int32)
+    batch = dict(coord=coord, feat=feat, segment=seg, offset=torch.tensor(np.cumsum(sizes)), index_valid_keys=["coord", "feat", "segment"])
+    tr = datasets.GridSample(grid_size=0.02, hash_type="fnv", mode="train", return_grid_coord=True, seed=1)
+    for _ in range(3):
+        out = tr(dict(batch))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = tr(dict(batch))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    n = coord.shape[0]
+    # algorithmic bytes per raw point: 2 x 12 B coord reads (extent, key), 24 B grid_coord + 8 B key out, 8 radix passes x 32 B
+    # (sort.cuh), run heads / ids / inverse ~ 60 B; per voxel: pick + payload gather ~ (8 + 12 + 24 + 24 + 4) x 2 B
+    bytes_alg = n * (24 + 32 + 8 * 32 + 60) + out["coord"].shape[0] * 144
+    return dict(workload=f"GridSample(0.02, fnv, train) + collate of {scenes} raw scenes, {n} raw points -> {out['coord'].shape[0]} voxels",
+                value=n / (ms * 1e-3), unit="raw points/s", ms=ms, bound="hbm", achieved=bytes_alg / (ms * 1e-3) / 1e9, peak=pk["hbm"],
+                frac=bytes_alg / (ms * 1e-3) / 1e9 / pk["hbm"], note="includes one host read (voxel counts) per call")
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -454,6 +509,10 @@ def run_ours(args):
                                               points_per_gpu=r["points_per_gpu"], steps=6, warmup=3)
         except Exception as e:  # supplementary lines never take the headline down
             supp["error"] = repr(e)[:300]
+        try:
+            supp["grid_sample"] = measure_grid_sample(args.scenes_per_gpu, args.voxels, dev, pk)
+        except Exception as e:
+            supp["grid_sample"] = dict(error=repr(e)[:300])
 
     # ---- the reference's GPU stack on the same box (stock flash-attn + torch-native rulebook conv) -------------
     gref = None

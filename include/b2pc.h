@@ -260,6 +260,17 @@ size_t b2pc_gelu_bwd_colsum_workspace_bytes(int64_t n, int c);
 int b2pc_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int64_t n, int c, void* dx, float* colsum, void* workspace,
                          size_t workspace_bytes, b2pc_stream_t stream);
 
+/* Fused cross-entropy of the segmentation head: nn.CrossEntropyLoss(reduction="mean", ignore_index) on logits [n, n_classes]
+ * (pointcept/models/losses/misc.py:13-40, called at pointcept/models/default.py:83-90).  target [n] int64.
+ * fwd: lse [n] fp32 (saved for backward), loss_count [2] fp32 = {mean loss over the non-ignored rows, their number};
+ * bwd: dlogits = (softmax(logits) - onehot(target)) * grad_loss[0] / count, zero on ignored rows; dlogits has the logits' dtype. */
+size_t b2pc_cross_entropy_workspace_bytes(int64_t n);
+int b2pc_cross_entropy_fwd(const void* logits, int dtype, const int64_t* target, int64_t n, int n_classes, int64_t ignore_index,
+                           float* lse, float* loss_count, void* workspace, size_t workspace_bytes, b2pc_stream_t stream);
+int b2pc_cross_entropy_bwd(const void* logits, int dtype, const int64_t* target, const float* lse, const float* grad_loss,
+                           const float* loss_count, int64_t n, int n_classes, int64_t ignore_index, void* dlogits,
+                           b2pc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * GPU voxelisation + collate: replaces the per-scene numpy GridSample transform
  * (pointcept/datasets/transform.py:840-958: floor(coord / grid_size), fnv_hash_vec :997-1011 /

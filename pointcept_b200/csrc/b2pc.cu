@@ -12,6 +12,7 @@
 #include "pool.cuh"
 #include "voxelize.cuh"
 #include "eval_ops.cuh"
+#include "loss.cuh"
 #ifndef B2PC_NO_UMMA
 #include "attn_umma.cuh"
 #include "spconv_umma.cuh"
@@ -451,6 +452,43 @@ int b2pc_gelu_bwd_colsum(const void* dy, const void* x, int dtype, int64_t n, in
   B2PC_PROF(stream, B2PC_P_OTHER, 0, 0);
   B2PC_CHECK_ARG(dy && x && dx && colsum && workspace, "gelu_bwd_colsum: null pointer");
   return launch_gelu_bwd_colsum(dy, x, dtype, n, c, dx, colsum, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- fused cross-entropy ------------------------------------------------------------------------------------------------------
+size_t b2pc_cross_entropy_workspace_bytes(int64_t n) { return cross_entropy_workspace_bytes(n); }
+
+int b2pc_cross_entropy_fwd(const void* logits, int dtype, const int64_t* target, int64_t n, int n_classes, int64_t ignore_index, float* lse,
+                           float* loss_count, void* workspace, size_t workspace_bytes, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, (double)n * (n_classes * (dtype == B2PC_F32 ? 4 : 2) + 12));
+  B2PC_CHECK_ARG(logits && target && lse && loss_count && workspace, "cross_entropy_fwd: null pointer");
+  B2PC_CHECK_ARG(n > 0 && n_classes >= 1 && dtype >= 0 && dtype <= 2, "cross_entropy_fwd: bad arguments");
+  if (workspace_bytes < cross_entropy_workspace_bytes(n)) { set_error("cross_entropy_fwd: workspace too small"); return B2PC_ERR_WORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = ce_blocks(n);
+  float* partial = (float*)workspace;
+  if (dtype == B2PC_F32) cross_entropy_fwd_kernel<float><<<blocks, kCeThreads, 0, s>>>((const float*)logits, target, n, n_classes, ignore_index, lse, partial);
+  else if (dtype == B2PC_F16) cross_entropy_fwd_kernel<__half><<<blocks, kCeThreads, 0, s>>>((const __half*)logits, target, n, n_classes, ignore_index, lse, partial);
+  else cross_entropy_fwd_kernel<__nv_bfloat16><<<blocks, kCeThreads, 0, s>>>((const __nv_bfloat16*)logits, target, n, n_classes, ignore_index, lse, partial);
+  cross_entropy_finish_kernel<<<1, 32, 0, s>>>(partial, blocks, loss_count);
+  count_launches(2);
+  B2PC_CHECK_LAUNCH("cross_entropy_fwd");
+  return B2PC_OK;
+}
+
+int b2pc_cross_entropy_bwd(const void* logits, int dtype, const int64_t* target, const float* lse, const float* grad_loss, const float* loss_count,
+                           int64_t n, int n_classes, int64_t ignore_index, void* dlogits, b2pc_stream_t stream) {
+  B2PC_PROF(stream, B2PC_P_OTHER, 0, (double)n * (2.0 * n_classes * (dtype == B2PC_F32 ? 4 : 2) + 12));
+  B2PC_CHECK_ARG(logits && target && lse && grad_loss && loss_count && dlogits, "cross_entropy_bwd: null pointer");
+  B2PC_CHECK_ARG(n > 0 && n_classes >= 1 && dtype >= 0 && dtype <= 2, "cross_entropy_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t b = ceil_div(n * n_classes, kCeThreads);
+  if (b > kNumSMs * 16) b = kNumSMs * 16;
+  if (dtype == B2PC_F32) cross_entropy_bwd_kernel<float><<<(unsigned)b, kCeThreads, 0, s>>>((const float*)logits, target, lse, grad_loss, loss_count, n, n_classes, ignore_index, (float*)dlogits);
+  else if (dtype == B2PC_F16) cross_entropy_bwd_kernel<__half><<<(unsigned)b, kCeThreads, 0, s>>>((const __half*)logits, target, lse, grad_loss, loss_count, n, n_classes, ignore_index, (__half*)dlogits);
+  else cross_entropy_bwd_kernel<__nv_bfloat16><<<(unsigned)b, kCeThreads, 0, s>>>((const __nv_bfloat16*)logits, target, lse, grad_loss, loss_count, n, n_classes, ignore_index, (__nv_bfloat16*)dlogits);
+  count_launches(1);
+  B2PC_CHECK_LAUNCH("cross_entropy_bwd");
+  return B2PC_OK;
 }
 
 // ---- GPU voxelisation / collate -----------------------------------------------------------------------------

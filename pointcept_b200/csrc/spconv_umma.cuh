@@ -8,12 +8,15 @@
 // cp.async, the matching W_k slice is staged next to it, and one thread issues KC/16 tcgen05.mma (M=128, N=n_tile,
 // K=16).  Offsets with no partner in the whole tile are skipped.  A ring of stages keeps several gathers in flight
 // while the tensor core drains earlier ones; stage reuse is gated by tcgen05.commit -> mbarrier.
-// Every output element is written once (deterministic) unless the launch is under-filled, in which case the offsets are
-// split over several CTAs per tile that add fp32 partials with red.global.add (order-dependent in the last fp32 bits).
+// Every output element is written once.  When the launch is under-filled (deep levels) the offsets are split over several CTAs per
+// tile; each split stores its fp32 partial tile to its own slice of a scratch buffer and a small kernel sums the slices in a fixed
+// order (deterministic; the round-1 red.global.add version was order-dependent and bound by L2 atomic throughput).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
 #include "attn_umma.cuh"  // UmmaFmt, pack2
+#include <cstring>
+#include <type_traits>
 
 namespace b2pc {
 
@@ -28,24 +31,44 @@ inline ConvUmmaCfg conv_umma_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   c.kc = c_in % 64 == 0 ? 64 : (c_in % 32 == 0 ? 32 : 16);
   // widest legal N tile (A rows are gathered once per N tile); when that leaves the GPU under-filled (deep, narrow-N
   // levels: a few dozen row tiles, 27 offsets x C/64 chunks of strictly sequential work each) the kernel offsets are split
-  // over `ksplit` CTAs per tile, which add their partial sums into an fp32 scratch with vector reductions
+  // over `ksplit` CTAs per tile, which store their partial sums to per-split slices of an fp32 scratch (summed afterwards)
   const int64_t m_tiles = ceil_div(n_out > 0 ? n_out : 1, kCuM);
+  // A/B knobs (tools/probe_conv.py sweeps them inside one process when B2PC_CONV_TUNE=1 was set at start-up; otherwise read once)
+  static const bool tune = [] { const char* e = getenv("B2PC_CONV_TUNE"); return e && atoi(e) != 0; }();
+  auto knob = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+  static const int nt0 = knob("B2PC_CONV_NT"), ks0 = knob("B2PC_CONV_KSPLIT"), ksx0 = knob("B2PC_CONV_KS");
+  const int env_nt = tune ? knob("B2PC_CONV_NT") : nt0;        // cap of the N tile (under-filled levels only)
+  const int env_ks = tune ? knob("B2PC_CONV_KSPLIT") : ks0;    // cap of the offset split
+  const int env_ksx = tune ? knob("B2PC_CONV_KS") : ksx0;      // exact offset split
+  int nt_cap = c_out <= 256 ? c_out : 256;
+  if (env_nt > 0 && m_tiles < 100 && nt_cap > env_nt) nt_cap = env_nt;   // only the under-filled (deep) levels are affected
   c.n_tile = 16;
-  for (int nt = c_out <= 256 ? c_out : 256; nt >= 16; nt -= 16)
+  for (int nt = nt_cap; nt >= 16; nt -= 16)
     if (c_out % nt == 0) { c.n_tile = nt; break; }
-  const int64_t ctas = m_tiles * (c_out / c.n_tile);
-  c.ksplit = 1;
-  if (ctas < 100 && kv > 1) {
-    int64_t ks = ceil_div(2 * kNumSMs, ctas);
-    if (ks > 9) ks = 9;
-    if (ks > kv) ks = kv;
-    c.ksplit = (int)ks;
-  }
   c.tmem_cols = 32;
   while (c.tmem_cols < c.n_tile) c.tmem_cols <<= 1;
   const int unit_bytes = kCuM * c.kc * 2 + c.n_tile * c.kc * 2;   // one ring stage: A tile + B tile of one (offset, chunk) unit
   c.idx_rows = kv < kCuMaxKV ? kv : kCuMaxKV;
   c.smem_bytes = c.idx_rows * kCuM * 4 + 256 + kCuMaxStages * unit_bytes;
+  // offset split of under-filled launches: CTAs per SM from shared memory / TMEM, then the split that minimises
+  //   waves(ctas * ks) * (offsets per CTA + fixed prologue/epilogue) + cost of summing ks partial tiles
+  // -- in particular never a split that spills a few CTAs into a second wave (30 tiles x 5 = 150 CTAs on 148 SMs)
+  const int64_t ctas = m_tiles * (c_out / c.n_tile);
+  int occ = (227 * 1024) / (c.smem_bytes + 1024);
+  if (occ > 512 / c.tmem_cols) occ = 512 / c.tmem_cols;
+  if (occ < 1) occ = 1;
+  const int64_t slots = (int64_t)kNumSMs * occ;
+  c.ksplit = 1;
+  if (ctas < slots && kv > 1) {
+    const int cap = env_ks > 0 ? env_ks : 16;
+    double best = 1e30;
+    for (int ks = 1; ks <= cap && ks <= kv; ++ks) {
+      const double waves = (double)ceil_div(ctas * ks, slots);
+      const double cost = waves * ((double)ceil_div(kv, ks) + 3.0) + 0.3 * ks;
+      if (cost < best - 1e-9) { best = cost; c.ksplit = ks; }
+    }
+    if (env_ksx > 0) c.ksplit = env_ksx < kv ? env_ksx : kv;
+  }
   return c;
 }
 
@@ -63,12 +86,16 @@ inline bool spconv_umma_supported(int dtype, int c_in, int c_out) {
 // MB: hand the staged tiles to the MMA-issuing thread through a per-stage `full` mbarrier (every thread's cp.async.mbarrier.arrive.noinc
 // fires when its copies of that stage have landed) instead of cp.async.wait_group + a block-wide barrier per iteration; only thread 0
 // waits, the other warps run ahead by up to the ring depth.
-template <typename T, int KC_T, int NT_T, int NCC_T, bool MB>
+// TB: the weight tile of a unit is ONE swizzled TMA box (rows of kc channels = the swizzle span) issued by one thread and tracked by a
+// per-stage byte-counting mbarrier, instead of 1-16 cp.async per thread: cp.async issue is the limiter of this kernel (each 16-byte
+// warp instruction costs ~30-50 cycles of LSU time), and at C >= 128 the weights are two thirds of those instructions.  K-major only:
+// the backward-data pass runs on a transposed copy of the weights (conv_transpose_w_kernel) so that both passes take this path.
+template <typename T, int KC_T, int NT_T, int NCC_T, bool MB, bool TB>
 __global__ void __launch_bounds__(kCuM)
 gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                         const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
                         int transpose_w, int flip, T* __restrict__ out, int kc_arg, int n_tile_arg, int tmem_cols, int idx_rows,
-                        int ksplit, float* __restrict__ acc) {
+                        int ksplit, float* __restrict__ acc, const __grid_constant__ CUtensorMap tmap_w) {
   using namespace umma;
   constexpr int S = kCuMaxStages;   // ring depth
   constexpr int PD = S - 2;         // prefetch distance: a refilled stage was consumed two iterations ago, so its MMAs are (almost
@@ -83,7 +110,9 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   uint32_t* tmem_slot = mask_s + 1;
   uint8_t* act_s = reinterpret_cast<uint8_t*>(tmem_slot + 1);   // [kCuMaxKV]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + idx_rows * kCuM * 4 + 128);   // [S] (MB only)
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + idx_rows * kCuM * 4 + 160);  // [S] (TB only): weight tile landed
   uint8_t* stage0 = smem + idx_rows * kCuM * 4 + 256;
+  if (TB) stage0 += (1024u - (smem_u32(stage0) & 1023u)) & 1023u;   // swizzled tiles: 1024-byte aligned atoms
   const int a_bytes = kCuM * kc * 2, b_bytes = n_tile * kc * 2, stage_bytes = a_bytes + b_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,7 +121,7 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
 
   if (warp == 0) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&bars[s], 1); if (MB) mbar_init(&full[s], kCuM); }
+    for (int s = 0; s < S; ++s) { mbar_init(&bars[s], 1); if (MB) mbar_init(&full[s], kCuM); if (TB) mbar_init(&wfull[s], 1); }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -103,7 +132,9 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   const uint32_t stage0_u32 = smem_u32(stage0);
 
   // ---- loop-invariant staging addresses -------------------------------------------------------------------------------------
-  // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16
+  // A: thread = row; kc/8 pieces of 16 B -> plane p at p*2048 + row*16.  (Letting the lanes of a warp sweep the pieces of a row first
+  // -- whole row segments per instruction, 4-8 x fewer L1 tag wavefronts -- was measured SLOWER on B200: 0.110 -> 0.119 ms at C = 32,
+  // 0.268 -> 0.336 ms at C = 64; the lanes then collide on the shared-memory banks of the plane layout.)
   const uint32_t a_dst0 = stage0_u32 + tid * 16;
   // B, K-major (forward): rows n (c_out side), kc contiguous channels; piece (n, p) -> p*(n_tile*16) + n*16; thread handles pieces
   // q = tid + i*128, i.e. p = tid % ppr (fixed) and n = tid / ppr + i * (128 / ppr)
@@ -127,8 +158,9 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   b_dst_step = rows_per_pass * 16;
   // UMMA descriptors of stage 0; other stages / K steps add a 16-byte-unit offset to the address field
   const uint64_t da0 = make_smem_desc(stage0_u32, kCuM * 16, 128);
-  const uint64_t db0 = transpose_w ? make_smem_desc(stage0_u32 + a_bytes, 128, kc * 16) : make_smem_desc(stage0_u32 + a_bytes, n_tile * 16, 128);
-  const uint32_t da_ks = (2 * kCuM * 16) >> 4, db_ks = (transpose_w ? 256 : 2 * n_tile * 16) >> 4, d_stage = stage_bytes >> 4;
+  const uint64_t db0 = TB ? make_smem_desc_swz(stage0_u32 + a_bytes, kc * 2)
+                          : (transpose_w ? make_smem_desc(stage0_u32 + a_bytes, 128, kc * 16) : make_smem_desc(stage0_u32 + a_bytes, n_tile * 16, 128));
+  const uint32_t da_ks = (2 * kCuM * 16) >> 4, db_ks = TB ? 2 : ((transpose_w ? 256 : 2 * n_tile * 16) >> 4), d_stage = stage_bytes >> 4;
 
   int gi = 0;                 // iterations issued so far (uniform); stage = gi % S, use count = gi / S
 
@@ -185,6 +217,14 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
 #pragma unroll
       for (int p = 0; p < (KC_T ? KC_T / 8 : 8); ++p)
         if (KC_T || p < kc / 8) cp_async16(a_dst + p * (kCuM * 16), g + p * 8, src >= 0);
+      if (TB) {
+        if (tid == 32) {   // one thread, one box: rows n0 .. n0+n_tile of the [c_out, kv*c_in] weight matrix, columns k*c_in + c0 .. +kc
+          mbar_expect_tx(&wfull[s], (uint32_t)b_bytes);
+          tma_load_2d(stage0_u32 + a_bytes + s_off, &tmap_w, k * c_in + c0, n0, &wfull[s]);
+        }
+        if (++ld_cc == n_cc) { ld_cc = 0; ++ld_a; }
+        return;
+      }
       const T* bs = b_src0 + (transpose_w ? ((int64_t)c0 * kv + k) * c_out : (int64_t)k * c_in + c0);
       uint32_t bd = b_dst0 + s_off;
       if (KC_T && NT_T) {
@@ -211,8 +251,9 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
     };
 
     auto issue_mma = [&](int g) {
-      tc_fence_after();
       const int s = g & (S - 1);
+      if (TB) mbar_wait(&wfull[s], (g / S) & 1);   // TMA writes through the async proxy: visible to the MMA once the bytes are counted
+      tc_fence_after();
       const uint64_t da = da0 + (uint64_t)(s * d_stage), db = db0 + (uint64_t)(s * d_stage);
 #pragma unroll
       for (int ks = 0; ks < (KC_T ? KC_T / 16 : 4); ++ks)
@@ -271,12 +312,11 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
       for (int i = 0; i < 16; ++i) r[i] = 0;
     }
     if (ksplit > 1) {
-      if (j < n_out && n_it > 0) {
-        float* dst = acc + j * c_out + n0 + cb;
+      if (j < n_out) {   // this split's partial tile goes to its own slice of the scratch with plain, full-sector stores (no atomics:
+                         // the sum over splits is formed in a fixed order by conv_split_finish_kernel)
+        uint4* dst = reinterpret_cast<uint4*>(acc + ((int64_t)blockIdx.z * n_out + j) * c_out + n0 + cb);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          red_add_v4(dst + 4 * i, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                     __uint_as_float(r[4 * i + 3]));
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
       }
     } else if (j < n_out) {
       uint32_t w[8];
@@ -296,13 +336,17 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// out[j, c] = acc[j, c] + bias[c]   (offset-split path)
+// out[j, c] = bias[c] + sum_z acc[z, j, c]   (offset-split path; fixed summation order)
 template <typename T>
 __global__ void __launch_bounds__(256)
-conv_split_finish_kernel(const float* __restrict__ acc, const T* __restrict__ bias, int64_t n_out, int c_out, T* __restrict__ out) {
+conv_split_finish_kernel(const float* __restrict__ acc, int n_split, const T* __restrict__ bias, int64_t n_out, int c_out, T* __restrict__ out) {
   const int64_t total = n_out * c_out / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(acc)[i];
+    float4 v = reinterpret_cast<const float4*>(acc)[i];
+    for (int z = 1; z < n_split; ++z) {
+      const float4 w = reinterpret_cast<const float4*>(acc)[(int64_t)z * total + i];
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
     const int c0 = (int)((i * 4) % c_out);
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
     if (bias) { b0 = to_f32(bias[c0]); b1 = to_f32(bias[c0 + 1]); b2 = to_f32(bias[c0 + 2]); b3 = to_f32(bias[c0 + 3]); }
@@ -310,10 +354,40 @@ conv_split_finish_kernel(const float* __restrict__ acc, const T* __restrict__ bi
   }
 }
 
+// wt[ci, k, co] = w[co, k, ci]: the backward-data pass as a forward pass over the transposed weights (K-major TMA tiles)
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_transpose_w_kernel(const T* __restrict__ w, int c_out, int kv, int c_in, T* __restrict__ wt) {
+  __shared__ T tile[32][33];
+  const int k = blockIdx.z, ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + tx;
+    if (co < c_out && ci < c_in) tile[r][tx] = w[((int64_t)co * kv + k) * c_in + ci];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + tx;
+    if (co < c_out && ci < c_in) wt[((int64_t)ci * kv + k) * c_out + co] = tile[tx][r];
+  }
+}
+
+inline bool conv_tma_weights_enabled() {
+  static const bool v = [] { const char* e = getenv("B2PC_CONV_TMAW"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+// shapes with compile-time tiles whose weight rows are one swizzle span (kc = 32 -> 64 B, kc = 64 -> 128 B)
+inline bool conv_tma_weights_shape(const ConvUmmaCfg& c) {
+  return conv_tma_weights_enabled() && (c.kc == 32 || c.kc == 64) &&
+         ((c.kc == 32 && c.n_tile == 32) || (c.kc == 64 && (c.n_tile == 64 || c.n_tile == 128 || c.n_tile == 256)));
+}
+
 inline size_t conv_umma_workspace_bytes(int64_t n_out, int c_in, int c_out, int kv) {
   if (c_in % 16 != 0 || c_out % 16 != 0) return 0;
   const ConvUmmaCfg c = conv_umma_cfg(n_out, c_in, c_out, kv);
-  return c.ksplit > 1 ? (size_t)n_out * c_out * sizeof(float) + 256 : 0;
+  size_t b = c.ksplit > 1 ? align_up((size_t)c.ksplit * n_out * c_out * sizeof(float), 256) : 0;
+  if (conv_tma_weights_shape(c)) b += align_up((size_t)kv * c_in * c_out * 2, 256);   // transposed weights of a backward-data call
+  return b ? b + 256 : 0;
 }
 
 template <typename T>
@@ -323,32 +397,54 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
   const ConvUmmaCfg c = conv_umma_cfg(n_out, c_in, c_out, kv);
   dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile, c.ksplit);
   float* acc = (float*)ws;
-  if (c.ksplit > 1) cudaMemsetAsync(acc, 0, (size_t)n_out * c_out * sizeof(float), stream);
-#define B2PC_CONV_LAUNCH_(KC, NT, NCC, MB)                                                                                           \
-  do {                                                                                                                             \
-    cudaFuncSetAttribute(gather_gemm_umma_kernel<T, KC, NT, NCC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes);      \
-    gather_gemm_umma_kernel<T, KC, NT, NCC, MB><<<grid, kCuM, c.smem_bytes, stream>>>(                                                 \
-        (const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,   \
-        c.kc, c.n_tile, c.tmem_cols, c.idx_rows, c.ksplit, acc);                                                                   \
-  } while (0)
+  const bool tb = conv_tma_weights_shape(c);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  int smem_bytes = c.smem_bytes;
+  if (tb) {
+    const void* wsrc = weight;
+    if (transpose_w) {   // weight is [c_in(arg) rows = conv c_out][kv][c_out(arg)]: make the [c_out(arg)][kv][c_in(arg)] copy this pass reads
+      T* wt = (T*)((char*)ws + (c.ksplit > 1 ? align_up((size_t)c.ksplit * n_out * c_out * sizeof(float), 256) : 0));
+      dim3 tg((unsigned)ceil_div(c_out, 32), (unsigned)ceil_div(c_in, 32), (unsigned)kv);
+      conv_transpose_w_kernel<T><<<tg, 256, 0, stream>>>((const T*)weight, c_in, kv, c_out, wt);
+      count_launches(1);
+      wsrc = wt;
+      transpose_w = 0;
+    }
+    if (!make_tile_tensor_map(&tmap, wsrc, std::is_same<T, __nv_bfloat16>::value, (uint64_t)c_out, (uint64_t)kv * c_in, (uint32_t)c.kc,
+                              (uint32_t)c.n_tile, c.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) {
+      set_error("spconv_gather_gemm: cuTensorMapEncodeTiled failed");
+      return B2PC_ERR_CUDA;
+    }
+    smem_bytes += 1024;   // alignment slack of the swizzled tiles
+  }
   static const bool conv_mb = [] { const char* e = getenv("B2PC_CONV_MB"); return e ? atoi(e) != 0 : false; }();   // measured on B200: the block barrier wins (profiles/README.md)
-#define B2PC_CONV_LAUNCH(KC, NT, NCC) do { if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false); } while (0)
+#define B2PC_CONV_LAUNCH_(KC, NT, NCC, MB, TB)                                                                                     \
+  do {                                                                                                                             \
+    cudaFuncSetAttribute(gather_gemm_umma_kernel<T, KC, NT, NCC, MB, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+    gather_gemm_umma_kernel<T, KC, NT, NCC, MB, TB><<<grid, kCuM, smem_bytes, stream>>>(                                           \
+        (const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,   \
+        c.kc, c.n_tile, c.tmem_cols, c.idx_rows, c.ksplit, acc, tmap);                                                             \
+  } while (0)
+#define B2PC_CONV_LAUNCH_T(KC, NT, NCC) do { if (tb) B2PC_CONV_LAUNCH_(KC, NT, NCC, false, true); else if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true, false); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false, false); } while (0)
+#define B2PC_CONV_LAUNCH(KC, NT, NCC) do { if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true, false); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false, false); } while (0)
   const int ncc = c_in / c.kc;
-  if (c.kc == 32 && c.n_tile == 32 && ncc == 1) B2PC_CONV_LAUNCH(32, 32, 1);
-  else if (c.kc == 64 && c.n_tile == 64 && ncc == 1) B2PC_CONV_LAUNCH(64, 64, 1);
-  else if (c.kc == 64 && c.n_tile == 128 && ncc == 2) B2PC_CONV_LAUNCH(64, 128, 2);
-  else if (c.kc == 64 && c.n_tile == 256 && ncc == 4) B2PC_CONV_LAUNCH(64, 256, 4);
-  else if (c.kc == 64 && c.n_tile == 64) B2PC_CONV_LAUNCH(64, 64, 0);
-  else if (c.kc == 64 && c.n_tile == 128) B2PC_CONV_LAUNCH(64, 128, 0);
-  else if (c.kc == 64 && c.n_tile == 256) B2PC_CONV_LAUNCH(64, 256, 0);
+  if (c.kc == 32 && c.n_tile == 32 && ncc == 1) B2PC_CONV_LAUNCH_T(32, 32, 1);
+  else if (c.kc == 64 && c.n_tile == 64 && ncc == 1) B2PC_CONV_LAUNCH_T(64, 64, 1);
+  else if (c.kc == 64 && c.n_tile == 128 && ncc == 2) B2PC_CONV_LAUNCH_T(64, 128, 2);
+  else if (c.kc == 64 && c.n_tile == 256 && ncc == 4) B2PC_CONV_LAUNCH_T(64, 256, 4);
+  else if (c.kc == 64 && c.n_tile == 64) B2PC_CONV_LAUNCH_T(64, 64, 0);
+  else if (c.kc == 64 && c.n_tile == 128) B2PC_CONV_LAUNCH_T(64, 128, 0);
+  else if (c.kc == 64 && c.n_tile == 256) B2PC_CONV_LAUNCH_T(64, 256, 0);
   else if (c.kc == 16 && c.n_tile == 32 && ncc == 1) B2PC_CONV_LAUNCH(16, 32, 1);
   else B2PC_CONV_LAUNCH(0, 0, 0);
+#undef B2PC_CONV_LAUNCH_T
 #undef B2PC_CONV_LAUNCH
 #undef B2PC_CONV_LAUNCH_
   if (c.ksplit > 1) {
     int64_t fb = ceil_div(n_out * c_out / 4, 256);
     if (fb > kNumSMs * 8) fb = kNumSMs * 8;
-    conv_split_finish_kernel<T><<<(int)fb, 256, 0, stream>>>(acc, (const T*)bias, n_out, c_out, (T*)out);
+    conv_split_finish_kernel<T><<<(int)fb, 256, 0, stream>>>(acc, c.ksplit, (const T*)bias, n_out, c_out, (T*)out);
     count_launches(1);
   }
   count_launches(1);

@@ -412,7 +412,10 @@ inline WgradWsCfg wgrad_ws_cfg(int64_t n_out, int c_in, int c_out, int kv) {
   while (c.tmem_cols < c.tpg * c.ncol) c.tmem_cols <<= 1;
   c.n_row_chunks = ceil_div(n_out > 0 ? n_out : 1, kWg2Rows);
   const int groups = c.n_mgroups * c.n_ntiles;
-  long long sp = ceil_div((long long)kNumSMs, groups);   // one persistent CTA per SM: the deep gather ring hides the latency
+  // one persistent CTA per SM (the deep gather ring hides the latency): the row range is split so that groups x splits fills the
+  // SMs in ONE wave -- rounding up (162 CTAs for 27 groups, 154 for 7, 216 for 108) left a second, nearly empty wave that doubled
+  // the runtime of the deep levels
+  long long sp = kNumSMs / groups;
   if (sp > c.n_row_chunks) sp = c.n_row_chunks;
   if (sp < 1) sp = 1;
   c.n_splits = (int)sp;

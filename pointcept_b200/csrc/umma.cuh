@@ -86,6 +86,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// K-major operand staged by TMA with a hardware swizzle (rows of `span` bytes = the swizzle span, 8-row atoms of 8*span bytes,
+// tile base aligned to 1024 B): layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (cute::UMMA::LayoutType); LBO is not
+// used by swizzled K-major layouts (set to 1), SBO = 8 * span = distance between 8-row groups.  A K step of 16 elements advances
+// the start address by 32 bytes inside the atom.
+__device__ __forceinline__ uint64_t make_smem_desc_swz(uint32_t smem_addr, uint32_t span_bytes) {
+  const uint64_t layout = span_bytes == 128 ? 2 : (span_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(((8 * span_bytes) >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 (32 bit):
 //   [4,6) D format: 1 = f32     [7,10) A format: 0 = f16, 1 = bf16     [10,13) B format
 //   [13] negate A  [14] negate B  [15] A major: 0 = K, 1 = MN   [16] B major   [17,23) N >> 3   [24,29) M >> 4
@@ -228,6 +243,30 @@ inline bool make_plane_tensor_map(CUtensorMap* map, const void* base, bool is_bf
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// host: general 2-D tiled tensor map over a row-major [rows, cols] matrix of 16-bit elements, box = box_rows x box_cols, with the
+// given shared-memory swizzle (box_cols * 2 bytes must equal the swizzle span: 128 B for SWIZZLE_128B, 64 B for SWIZZLE_64B).
+inline bool make_tile_tensor_map(CUtensorMap* map, const void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                                 uint32_t box_rows, CUtensorMapSwizzle swizzle) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeFn)p;
+  }();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
+            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

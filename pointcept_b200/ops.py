@@ -850,3 +850,40 @@ def rope_qkv(qkv, pos, base=100.0, f0=1.0):
     pos = pos if (pos.dtype == torch.int64 and pos.is_contiguous()) else pos.long().contiguous()
     assert pos.shape[0] == qkv.shape[0]
     return _RopeQKV.apply(qkv, pos, float(base), float(f0))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused cross-entropy (pointcept/models/losses/misc.py:13-40)
+# ------------------------------------------------------------------------------------------------
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        _need_cuda(logits, target)
+        logits = logits.contiguous()
+        target = target if (target.dtype == torch.int64 and target.is_contiguous()) else target.long().contiguous()
+        n, c = logits.shape
+        L = _lib.lib()
+        lse = torch.empty(n, dtype=torch.float32, device=logits.device)
+        loss_count = torch.empty(2, dtype=torch.float32, device=logits.device)
+        ws = _ws(L.b2pc_cross_entropy_workspace_bytes(n), logits.device)
+        _lib.check(L.b2pc_cross_entropy_fwd(_p(logits), _DTYPES[logits.dtype], _p(target), n, c, int(ignore_index), _p(lse), _p(loss_count), _p(ws),
+                                            ws.numel(), _stream()), "cross_entropy_fwd")
+        ctx.save_for_backward(logits, target, lse, loss_count)
+        ctx.ignore_index = int(ignore_index)
+        return loss_count[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, lse, loss_count = ctx.saved_tensors
+        n, c = logits.shape
+        g = g.detach().float().reshape(1).contiguous()
+        d = torch.empty_like(logits)
+        _lib.check(_lib.lib().b2pc_cross_entropy_bwd(_p(logits), _DTYPES[logits.dtype], _p(target), _p(lse), _p(g), _p(loss_count), n, c,
+                                                     ctx.ignore_index, _p(d), _stream()), "cross_entropy_bwd")
+        return d, None, None
+
+
+def cross_entropy(logits, target, ignore_index=-1):
+    """nn.functional.cross_entropy(logits, target, ignore_index=...) with reduction="mean" -> scalar fp32 loss."""
+    assert logits.dim() == 2 and target.dim() == 1 and target.shape[0] == logits.shape[0] and logits.shape[0] > 0
+    return _CrossEntropy.apply(logits, target, ignore_index)

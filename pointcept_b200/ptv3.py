@@ -680,6 +680,9 @@ class PointTransformerV3(PointModule):
         return point
 
 
+_FUSED_LOSS = os.environ.get("B2PC_LOSS_FUSED", "1") != "0"
+
+
 class PTv3Segmentor(nn.Module):
     """backbone + linear head + cross-entropy: the part of DefaultSegmentorV2 (pointcept/models/default.py:41-95)
     the fwd+bwd benchmark needs.  Parameter names match (``backbone.*``, ``seg_head.*``)."""
@@ -697,7 +700,10 @@ class PTv3Segmentor(nn.Module):
         seg_logits = self.seg_head(point.feat)
         out = dict(seg_logits=seg_logits)
         if "segment" in input_dict:
-            out["loss"] = nn.functional.cross_entropy(seg_logits.float(), input_dict["segment"], ignore_index=-1)
+            if _FUSED_LOSS and seg_logits.is_cuda:    # one pass each way (csrc/loss.cuh) instead of log_softmax + nll_loss
+                out["loss"] = ops.cross_entropy(seg_logits, input_dict["segment"], ignore_index=-1)
+            else:
+                out["loss"] = nn.functional.cross_entropy(seg_logits.float(), input_dict["segment"], ignore_index=-1)
         return out
 
 

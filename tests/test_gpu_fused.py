@@ -288,3 +288,27 @@ def test_fused_adamw_matches_torch_adamw_over_several_steps():
     for a, b in zip(ps1, ps2):
         assert rel_l2(o1.state[a]["exp_avg"], o2.state[b]["exp_avg"]) < 1e-6
         assert rel_l2(o1.state[a]["exp_avg_sq"], o2.state[b]["exp_avg_sq"]) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_fused_cross_entropy_matches_torch(dtype):
+    """csrc/loss.cuh vs nn.functional.cross_entropy(logits.float(), target, ignore_index=-1) (losses/misc.py:13-40): the loss to
+    1e-6 relative (fp32 math on the same rounded logits), the gradient to the output dtype's rounding."""
+    gen = torch.Generator().manual_seed(0)
+    for n, c in ((5000, 20), (777, 200), (33, 3)):
+        logits = (torch.randn(n, c, generator=gen) * 3).to(dtype)
+        target = torch.randint(0, c, (n,), generator=gen)
+        target[torch.rand(n, generator=gen) < 0.2] = -1
+        x = logits.cuda().requires_grad_(True)
+        loss = ops.cross_entropy(x, target.cuda(), ignore_index=-1)
+        (loss * 1.7).backward()
+        ref = logits.float().requires_grad_(True)
+        want = torch.nn.functional.cross_entropy(ref, target, ignore_index=-1)
+        (want * 1.7).backward()
+        assert abs(float(loss) - float(want)) <= 2e-6 * max(1.0, abs(float(want)))
+        tol = {torch.float32: 2e-6, torch.bfloat16: 4e-3, torch.float16: 5e-4}[dtype]   # fp32: expf / logf of the device vs the host library
+        assert float((x.grad.float().cpu() - ref.grad).abs().max()) <= tol * max(float(ref.grad.abs().max()), 1e-6) + 1e-9
+        assert x.grad.dtype == dtype
+    # every row ignored -> NaN like torch
+    x = torch.randn(8, 5, device="cuda")
+    assert torch.isnan(ops.cross_entropy(x, torch.full((8,), -1, device="cuda"), ignore_index=-1))

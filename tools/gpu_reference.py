@@ -102,7 +102,8 @@ def reference_gpu_ops():
     saved = dict(sparse_conv=ops.sparse_conv, layer_norm_supported=ops.layer_norm_supported, segment_max=ops.segment_max,
                  unpool_add=ops.unpool_add, drop_path_add=ops.drop_path_add, binding=ops.binding)
     saved_ptv3 = dict(fa=_ptv3.flash_attn_varlen_qkvpacked_func, g=_ptv3.serialized_gather, s=_ptv3.serialized_scatter_back,
-                      fl=_ptv3.FusedLinear.use_fused_bias_grad)
+                      fl=_ptv3.FusedLinear.use_fused_bias_grad, loss=_ptv3._FUSED_LOSS)
+    _ptv3._FUSED_LOSS = False
     ops.sparse_conv = native_sparse_conv
     ops.layer_norm_supported = lambda x, c: False
     ops.segment_max = _segment_max
@@ -121,6 +122,7 @@ def reference_gpu_ops():
         _ptv3.flash_attn_varlen_qkvpacked_func = saved_ptv3["fa"]
         _ptv3.serialized_gather, _ptv3.serialized_scatter_back = saved_ptv3["g"], saved_ptv3["s"]
         _ptv3.FusedLinear.use_fused_bias_grad = saved_ptv3["fl"]
+        _ptv3._FUSED_LOSS = saved_ptv3["loss"]
 
 
 DESCRIPTION = ("same step on the reference's GPU stack: stock flash-attn {fa} (FA2 mma.sync kernels, sm_100 cubin) for the patch "

@@ -30,12 +30,12 @@ def main():
     bid = np.repeat(np.arange(2), np.diff(b["offset"], prepend=0))
     levels = []
     g, bb = grid, bid
-    for s in range(4):
+    for s in range(5):
         levels.append((g, bb))
         key = np.concatenate([bb[:, None], g >> 1], 1)
         u = np.unique(key, axis=0)
         bb, g = u[:, 0], u[:, 1:]
-    cfgs = [(0, 32, 3), (0, 64, 3), (1, 64, 3), (2, 128, 3), (3, 256, 3), (0, 16, 5)]
+    cfgs = [(0, 32, 3), (0, 64, 3), (1, 64, 3), (2, 128, 3), (3, 256, 3), (0, 16, 5), (4, 512, 3)]
     impls = [int(x) for x in os.environ.get("IMPLS", "1,2").split(",")]
     if "ONLY" in os.environ:
         cfgs = [cfgs[int(i)] for i in os.environ["ONLY"].split(",")]

@@ -79,6 +79,13 @@ inline bool spconv_umma_supported(int dtype, int c_in, int c_out) {
   return true;
 }
 
+// tile::gather4 maps of the feature matrix, one per channel chunk: map i views columns [i*kc, (i+1)*kc) (base pointer advanced, row
+// stride unchanged) so that the gather always reads from column 0.  (A single map with a non-zero column coordinate returned wrong
+// data on B200 for every chunk but the first -- measured, tools/conv_ta_check.py; the box of a gather4 map is {kc, 1}: four rows
+// in the box is an illegal instruction.)
+constexpr int kCuMaxChunks = 8;
+struct ConvGatherMaps { CUtensorMap m[kCuMaxChunks]; };
+
 // KC_T / NT_T: compile-time channel chunk and N tile for the common layer widths (0 = use the runtime arguments); NCC_T: compile-time
 // number of channel chunks per offset (0 = runtime).  The specialisations fold the address arithmetic of the staging loops; the
 // ring depth is a compile-time constant and the (offset, chunk) cursor advances incrementally, so the per-iteration instruction
@@ -90,12 +97,19 @@ inline bool spconv_umma_supported(int dtype, int c_in, int c_out) {
 // per-stage byte-counting mbarrier, instead of 1-16 cp.async per thread: cp.async issue is the limiter of this kernel (each 16-byte
 // warp instruction costs ~30-50 cycles of LSU time), and at C >= 128 the weights are two thirds of those instructions.  K-major only:
 // the backward-data pass runs on a transposed copy of the weights (conv_transpose_w_kernel) so that both passes take this path.
-template <typename T, int KC_T, int NT_T, int NCC_T, bool MB, bool TB>
+// TA (with TB): the gathered rows come by TMA too -- tile::gather4, four rulebook rows per instruction, one instruction per lane of a
+// producer warp per unit, absent pairs (-1) as out-of-range rows that the TMA zero-fills; the tile is then a swizzled K-major operand
+// like the weights.  No thread issues cp.async any more: warp 1 produces, thread 0 issues the MMAs, both synchronise through the
+// per-stage mbarriers only (no block barrier, no wait_group in the loop).  Measured on B200 (profiles/README.md): bit-correct, but the
+// TMA unit retires only about one gather4 per 44 cycles per SM (C = 32: 0.103 -> 0.247 ms, C = 64: 0.198 -> 0.292 ms), so cp.async with
+// thread = row stays the default for the gathered operand and B2PC_CONV_TMAA=1 selects this path.
+template <typename T, int KC_T, int NT_T, int NCC_T, bool MB, bool TB, bool TA>
 __global__ void __launch_bounds__(kCuM)
 gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight, const T* __restrict__ bias,
                         const int32_t* __restrict__ pair, int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv,
                         int transpose_w, int flip, T* __restrict__ out, int kc_arg, int n_tile_arg, int tmem_cols, int idx_rows,
-                        int ksplit, float* __restrict__ acc, const __grid_constant__ CUtensorMap tmap_w) {
+                        int ksplit, float* __restrict__ acc, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvGatherMaps tmap_f,
+                        int n_in) {
   using namespace umma;
   constexpr int S = kCuMaxStages;   // ring depth
   constexpr int PD = S - 2;         // prefetch distance: a refilled stage was consumed two iterations ago, so its MMAs are (almost
@@ -122,6 +136,7 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   if (warp == 0) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&bars[s], 1); if (MB) mbar_init(&full[s], kCuM); if (TB) mbar_init(&wfull[s], 1); }
+    if (TA) mbar_init(&full[0], 1);   // TA: `all MMAs done` (the idle warps cannot use the ring barriers: see below)
     fence_mbar_init();
   }
   tc_fence_before();
@@ -157,10 +172,10 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
   }
   b_dst_step = rows_per_pass * 16;
   // UMMA descriptors of stage 0; other stages / K steps add a 16-byte-unit offset to the address field
-  const uint64_t da0 = make_smem_desc(stage0_u32, kCuM * 16, 128);
+  const uint64_t da0 = TA ? make_smem_desc_swz(stage0_u32, kc * 2) : make_smem_desc(stage0_u32, kCuM * 16, 128);
   const uint64_t db0 = TB ? make_smem_desc_swz(stage0_u32 + a_bytes, kc * 2)
                           : (transpose_w ? make_smem_desc(stage0_u32 + a_bytes, 128, kc * 16) : make_smem_desc(stage0_u32 + a_bytes, n_tile * 16, 128));
-  const uint32_t da_ks = (2 * kCuM * 16) >> 4, db_ks = TB ? 2 : ((transpose_w ? 256 : 2 * n_tile * 16) >> 4), d_stage = stage_bytes >> 4;
+  const uint32_t da_ks = TA ? 2 : ((2 * kCuM * 16) >> 4), db_ks = TB ? 2 : ((transpose_w ? 256 : 2 * n_tile * 16) >> 4), d_stage = stage_bytes >> 4;
 
   int gi = 0;                 // iterations issued so far (uniform); stage = gi % S, use count = gi / S
 
@@ -205,6 +220,39 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
     if (tid < n_act) act_s[tid] = (uint8_t)__fns(mask, 0, tid + 1);   // active offsets of this chunk, in order
     __syncthreads();
 
+    if (TA) {
+      if (warp == 1) {          // ---- producer warp: one gather4 per lane (rows 4*lane .. 4*lane+3) + one weight box per unit
+        int pa = 0, pc = 0;
+        for (int it = 0; it < n_it; ++it) {
+          const int g = gi + it, s = g & (S - 1);
+          if (g >= S) mbar_wait(&bars[s], ((g / S) - 1) & 1);          // the MMAs that read this stage S units ago have completed
+          const int kl = act_s[pa];
+          const int c0 = pc * kc;   // weights: column of the [c_out, kv*c_in] matrix; features: one map per channel chunk (see ConvGatherMaps)
+          const uint32_t st = stage0_u32 + s * stage_bytes;
+          if (lane == 0) {
+            mbar_expect_tx(&wfull[s], (uint32_t)(a_bytes + b_bytes));
+            tma_load_2d(st + a_bytes, &tmap_w, (kb + kl) * c_in + c0, n0, &wfull[s]);
+          }
+          const int4 r4 = *reinterpret_cast<const int4*>(idx_s + kl * kCuM + 4 * lane);
+          tma_gather4(st + lane * (4 * kc * 2), &tmap_f.m[pc], 0, r4.x >= 0 ? r4.x : n_in, r4.y >= 0 ? r4.y : n_in, r4.z >= 0 ? r4.z : n_in,
+                      r4.w >= 0 ? r4.w : n_in, &wfull[s]);
+          if (++pc == n_cc) { pc = 0; ++pa; }
+        }
+      } else if (tid == 0) {    // ---- MMA issuer
+        for (int it = 0; it < n_it; ++it) {
+          const int g = gi + it, s = g & (S - 1);
+          mbar_wait(&wfull[s], (g / S) & 1);
+          tc_fence_after();
+          const uint64_t da = da0 + (uint64_t)(s * d_stage), db = db0 + (uint64_t)(s * d_stage);
+#pragma unroll
+          for (int ks = 0; ks < (KC_T ? KC_T / 16 : 4); ++ks)
+            if (KC_T || ks < kc / 16) mma_ss(tmem_base, da + ks * da_ks, db + ks * db_ks, idesc, (g > 0 || ks > 0) ? 1u : 0u);
+          mma_commit(&bars[s]);
+        }
+      }
+      gi += n_it;
+      continue;
+    }
     int ld_a = 0, ld_cc = 0;   // cursor of the next unit to load: index into act_s, channel chunk
     auto issue_loads = [&](int s) {
       const int kl = act_s[ld_a];                     // offset inside the chunk
@@ -297,7 +345,17 @@ gather_gemm_umma_kernel(const T* __restrict__ feat, const T* __restrict__ weight
     cp_async_wait<0>();
   }
   const int n_it = gi;
-  if (gi > 0) mbar_wait(&bars[(gi - 1) & (S - 1)], ((gi - 1) / S) & 1);
+  if (TA) {
+    // the warps that neither produce nor issue arrive here at once; a parity wait on a ring barrier that is still several phases
+    // behind would fall through (parity 1 of a barrier in phase 0 reads as "the preceding phase", which counts as complete), so the
+    // end of the accumulation is signalled on a barrier of its own, used exactly once
+    if (gi > 0) {
+      if (tid == 0) mma_commit(&full[0]);
+      mbar_wait(&full[0], 0);
+    }
+  } else if (gi > 0) {
+    mbar_wait(&bars[(gi - 1) & (S - 1)], ((gi - 1) / S) & 1);
+  }
   tc_fence_after();
   // epilogue: thread = row, 16 columns at a time
   const int64_t j = row0 + tid;
@@ -392,7 +450,7 @@ inline size_t conv_umma_workspace_bytes(int64_t n_out, int c_in, int c_out, int 
 
 template <typename T>
 inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const void* bias, const int32_t* pair,
-                                     int64_t pair_stride, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip,
+                                     int64_t pair_stride, int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip,
                                      void* out, void* ws, cudaStream_t stream) {
   const ConvUmmaCfg c = conv_umma_cfg(n_out, c_in, c_out, kv);
   dim3 grid((unsigned)ceil_div(n_out, kCuM), c_out / c.n_tile, c.ksplit);
@@ -418,16 +476,29 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
     }
     smem_bytes += 1024;   // alignment slack of the swizzled tiles
   }
+  static const int conv_ta = [] { const char* e = getenv("B2PC_CONV_TMAA"); return e ? atoi(e) : 0; }();        // 1: gathered rows by tile::gather4 (correct, but measured slower than cp.async on B200)
+  const bool ta = tb && conv_ta != 0 && c_in / c.kc <= kCuMaxChunks;
+  ConvGatherMaps tmapf;
+  memset(&tmapf, 0, sizeof(tmapf));
+  if (ta) {
+    for (int i = 0; i < c_in / c.kc; ++i) {
+      if (!make_gather4_tensor_map(&tmapf.m[i], (const T*)feat + (size_t)i * c.kc, std::is_same<T, __nv_bfloat16>::value, (uint64_t)n_in,
+                                   (uint64_t)c_in, (uint32_t)c.kc, c.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) {
+        set_error("spconv_gather_gemm: cuTensorMapEncodeTiled (gather4 map) failed");
+        return B2PC_ERR_CUDA;
+      }
+    }
+  }
   static const bool conv_mb = [] { const char* e = getenv("B2PC_CONV_MB"); return e ? atoi(e) != 0 : false; }();   // measured on B200: the block barrier wins (profiles/README.md)
-#define B2PC_CONV_LAUNCH_(KC, NT, NCC, MB, TB)                                                                                     \
+#define B2PC_CONV_LAUNCH_(KC, NT, NCC, MB, TB, TA)                                                                                    \
   do {                                                                                                                             \
-    cudaFuncSetAttribute(gather_gemm_umma_kernel<T, KC, NT, NCC, MB, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
-    gather_gemm_umma_kernel<T, KC, NT, NCC, MB, TB><<<grid, kCuM, smem_bytes, stream>>>(                                           \
+    cudaFuncSetAttribute(gather_gemm_umma_kernel<T, KC, NT, NCC, MB, TB, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+    gather_gemm_umma_kernel<T, KC, NT, NCC, MB, TB, TA><<<grid, kCuM, smem_bytes, stream>>>(                                           \
         (const T*)feat, (const T*)weight, (const T*)bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, (T*)out,   \
-        c.kc, c.n_tile, c.tmem_cols, c.idx_rows, c.ksplit, acc, tmap);                                                             \
+        c.kc, c.n_tile, c.tmem_cols, c.idx_rows, c.ksplit, acc, tmap, tmapf, (int)n_in);                                                             \
   } while (0)
-#define B2PC_CONV_LAUNCH_T(KC, NT, NCC) do { if (tb) B2PC_CONV_LAUNCH_(KC, NT, NCC, false, true); else if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true, false); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false, false); } while (0)
-#define B2PC_CONV_LAUNCH(KC, NT, NCC) do { if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true, false); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false, false); } while (0)
+#define B2PC_CONV_LAUNCH_T(KC, NT, NCC) do { if (ta) B2PC_CONV_LAUNCH_(KC, NT, NCC, false, true, true); else if (tb) B2PC_CONV_LAUNCH_(KC, NT, NCC, false, true, false); else if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true, false, false); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false, false, false); } while (0)
+#define B2PC_CONV_LAUNCH(KC, NT, NCC) do { if (conv_mb) B2PC_CONV_LAUNCH_(KC, NT, NCC, true, false, false); else B2PC_CONV_LAUNCH_(KC, NT, NCC, false, false, false); } while (0)
   const int ncc = c_in / c.kc;
   if (c.kc == 32 && c.n_tile == 32 && ncc == 1) B2PC_CONV_LAUNCH_T(32, 32, 1);
   else if (c.kc == 64 && c.n_tile == 64 && ncc == 1) B2PC_CONV_LAUNCH_T(64, 64, 1);
@@ -455,11 +526,10 @@ inline int launch_gather_gemm_umma_t(const void* feat, const void* weight, const
 inline int launch_gather_gemm_umma(const void* feat, const void* weight, const void* bias, const int32_t* pair, int64_t pair_stride,
                                    int64_t n_in, int64_t n_out, int c_in, int c_out, int kv, int transpose_w, int flip, int dtype,
                                    void* out, void* ws, cudaStream_t stream) {
-  (void)n_in;
   if (n_out == 0) return B2PC_OK;
   if (dtype == B2PC_BF16)
-    return launch_gather_gemm_umma_t<__nv_bfloat16>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, ws, stream);
-  return launch_gather_gemm_umma_t<__half>(feat, weight, bias, pair, pair_stride, n_out, c_in, c_out, kv, transpose_w, flip, out, ws, stream);
+    return launch_gather_gemm_umma_t<__nv_bfloat16>(feat, weight, bias, pair, pair_stride, n_in, n_out, c_in, c_out, kv, transpose_w, flip, out, ws, stream);
+  return launch_gather_gemm_umma_t<__half>(feat, weight, bias, pair, pair_stride, n_in, n_out, c_in, c_out, kv, transpose_w, flip, out, ws, stream);
 }
 
 }  // namespace b2pc

@@ -49,6 +49,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
                : "memory");
 }
 
+// tile::gather4: four arbitrary rows of a 2-D tensor (row coordinates r0..r3, all at column `col`) land as four consecutive rows of the
+// destination tile, swizzled like a tiled box; rows outside the tensor are filled with zeros.  Completes 4 * box_cols * 2 bytes.
+__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+               ::"r"(smem_dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // generic-proxy writes (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -264,6 +272,30 @@ inline bool make_tile_tensor_map(CUtensorMap* map, const void* base, bool is_bf1
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
   const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
+            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// host: tile::gather4 map over the column window [0, box_cols) of a row-major matrix whose rows are row_stride_elems apart: box =
+// {box_cols, 1} (the four rows of a gather come from the instruction's coordinates)
+inline bool make_gather4_tensor_map(CUtensorMap* map, const void* base, bool is_bf16, uint64_t rows, uint64_t row_stride_elems,
+                                    uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeFn)p;
+  }();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {box_cols, rows};
+  const cuuint64_t strides[1] = {row_stride_elems * 2};
+  const cuuint32_t box[2] = {box_cols, 1};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

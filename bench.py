@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--gpu-reference-steps", type=int, default=5)
     ap.add_argument("--bucket-mb", type=int, default=100, help="DDP gradient bucket size")
     ap.add_argument("--no-static-graph", action="store_true", help="DDP without static_graph")
+    ap.add_argument("--grad-exchange", default="flat", choices=["flat", "ddp"],
+                    help="N > 1: pointcept_b200.reducer.FlatGradReducer (one hook, two collectives per step) or torch DDP")
+    ap.add_argument("--force-dist", action="store_true",
+                    help="N = 1 only: initialise NCCL with world size 1 and run the gradient exchange anyway (measures its overhead)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler (CUPTI) per-kernel breakdown of two extra steps to this file")
     ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of pointcept_b200.optim.FusedAdamW")
     return ap.parse_args()
@@ -246,8 +250,12 @@ def measure(args, workload, scenes, voxels, steps, warmup, kind="indoor", want_p
     in_ch, n_cls = (4, 16) if kind == "lidar" else (6, 20)
     model = build_model(workload, dev, args, in_ch, n_cls)
     n_params = sum(p.numel() for p in model.parameters())
-    net = model
-    if world > 1 and not reference_stack:
+    net, reducer = model, None
+    dist_on = world > 1 or (args.force_dist and dist.is_initialized())
+    if dist_on and not reference_stack and args.grad_exchange == "flat":
+        from pointcept_b200.reducer import FlatGradReducer     # the gradient all-reduce of engines/defaults.py:22-43, flat + overlapped
+        reducer = FlatGradReducer(model.parameters())
+    elif dist_on and not reference_stack:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True,
                                                         bucket_cap_mb=args.bucket_mb, static_graph=not args.no_static_graph)
     if reference_stack or args.torch_adamw:
@@ -276,6 +284,8 @@ def measure(args, workload, scenes, voxels, steps, warmup, kind="indoor", want_p
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = net(d)
         out["loss"].backward()
+        if reducer is not None:
+            reducer.finish()
         opt.step()
         return out["loss"]
 
@@ -390,7 +400,13 @@ def measure(args, workload, scenes, voxels, steps, warmup, kind="indoor", want_p
             dt = allmax(time.perf_counter() - t0)
             res["e2e_value"] = total_points * steps / dt
             res["loss_last"] = float(loss_pinned[-1])
-    del net, model, opt
+    if reducer is not None:
+        res["grad_exchange"] = dict(kind="flat", steps=reducer.stats["steps"], overlapped_steps=reducer.stats["early_steps"],
+                                    early_bytes=4 * reducer.early_end, total_bytes=4 * reducer.flat.numel())
+        reducer.remove()
+    elif dist_on and not reference_stack:
+        res["grad_exchange"] = dict(kind="ddp", bucket_mb=args.bucket_mb, static_graph=not args.no_static_graph)
+    del net, model, opt, reducer
     torch.cuda.empty_cache()
     return res
 
@@ -478,9 +494,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 operators have no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 or args.force_dist:
         os.environ.setdefault("NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", device_id=dev, rank=rank, world_size=world)
     if args.kernel_impl is not None:
         ops.set_impl(args.kernel_impl)
     if args.fused_linear:
@@ -555,6 +573,7 @@ def run_ours(args):
                                + f"{args.scenes_per_gpu} synthetic ScanNet-scale scenes per GPU",
                    "scenes_per_gpu": args.scenes_per_gpu, "points_per_gpu": main["points_per_gpu"], "global_points": int(main["total_points"]),
                    "params_M": main["params_M"], "patch_size": 1024, "orders": 4, "parallelism": f"dp{world}",
+                   "grad_exchange": main.get("grad_exchange"),
                    "l2": "no explicit flush: one step streams several GB of activations, far beyond the 126 MB L2",
                    "kernel_impl": ops.get_impl(), "spatial_reorder": not args.no_reorder, "loss_last": main.get("loss_last"),
                    "binding": "compiled" if ops.binding() is not None else "ctypes"},
@@ -569,7 +588,7 @@ def run_ours(args):
         "supplementary": supp,
     }
     print(json.dumps(line))
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

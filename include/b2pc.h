@@ -241,7 +241,9 @@ int b2pc_fused_residual_bwd(const float* dr_out, const void* dr16, const void* d
 
 /* One launch refreshes the half-precision shadows of a list of fp32 parameter tensors (what autocast does with one cast
  * kernel per weight per step, torch/amp).  plan: DEVICE array of n_items records {const float* src; void* dst;
- * long long count; long long first_block} with first_block the running sum of ceil(count / 2048); total_blocks its end. */
+ * long long count; long long first_block} with first_block the running sum of ceil(count / 2048); total_blocks its end.
+ * dst_dtype B2PC_F16 / B2PC_BF16: cast; B2PC_F32: plain multi-tensor copy (packs the gradients of a parameter list into the
+ * flat buffer of the data-parallel all-reduce, the exchange step of pointcept/engines/defaults.py:22-43). */
 int b2pc_multi_cast(const void* plan_device, int n_items, long long total_blocks, int dst_dtype, b2pc_stream_t stream);
 
 /* AdamW (torch.optim.AdamW semantics: decoupled weight decay, per-tensor bias correction) over a whole parameter list in one

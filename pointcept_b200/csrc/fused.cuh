@@ -389,9 +389,11 @@ multi_cast_kernel(const CastItem* __restrict__ plan, int n_items) {
 
 inline int launch_multi_cast(const void* plan, int n_items, long long total_blocks, int dst_dtype, cudaStream_t stream) {
   B2PC_CHECK_ARG(plan && n_items >= 0 && total_blocks >= 0, "multi_cast: bad arguments");
-  B2PC_CHECK_ARG(dst_dtype == B2PC_F16 || dst_dtype == B2PC_BF16, "multi_cast: destination dtype must be fp16 or bf16");
+  B2PC_CHECK_ARG(dst_dtype == B2PC_F16 || dst_dtype == B2PC_BF16 || dst_dtype == B2PC_F32, "multi_cast: unknown destination dtype %d", dst_dtype);
   if (n_items == 0 || total_blocks == 0) return B2PC_OK;
   if (dst_dtype == B2PC_BF16) multi_cast_kernel<__nv_bfloat16><<<(unsigned)total_blocks, 256, 0, stream>>>((const CastItem*)plan, n_items);
+  else if (dst_dtype == B2PC_F32)   // plain multi-tensor copy: packs a list of gradients into one flat all-reduce buffer (reducer.py)
+    multi_cast_kernel<float><<<(unsigned)total_blocks, 256, 0, stream>>>((const CastItem*)plan, n_items);
   else multi_cast_kernel<__half><<<(unsigned)total_blocks, 256, 0, stream>>>((const CastItem*)plan, n_items);
   count_launches(1);
   B2PC_CHECK_LAUNCH("multi_cast");

@@ -396,3 +396,49 @@ def test_drop_path_add_semantics():
     assert torch.equal(x.grad[dropped].float(), torch.zeros_like(x.grad[dropped].float()))
     assert rel_l2(x.grad[kept].float(), torch.full_like(x.grad[kept].float(), 1 / (1 - p))) < 5e-3
     assert torch.equal(ops.drop_path_add(s, x.detach(), p, False), s + x.detach())
+
+
+def test_flat_grad_reducer_nccl_packs_bit_exact_and_feeds_fused_adamw(golden_dir):
+    """pointcept_b200/reducer.py on the GPU (NCCL, world size 1 inside this process: the average over one rank is the identity):
+    the one-launch pack (b2pc_multi_cast, fp32 destination) copies every gradient bit-exactly into the arrival-order flat buffer,
+    the early group is exchanged from the autograd hook, p.grad become slices of the buffer and FusedAdamW steps from them exactly
+    as it does from the loose gradients.  The N > 1 protocol itself is covered under gloo (tests/test_host_logic.py)."""
+    import torch.distributed as dist
+    from pointcept_b200.optim import FusedAdamW
+    from pointcept_b200.reducer import FlatGradReducer
+    g = np.load(os.path.join(golden_dir, "ptv3_tiny.npz"))
+    sd = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}
+    data = dict(coord=torch.from_numpy(g["coord"]).to(DEV), grid_coord=torch.from_numpy(g["grid_coord"]).to(DEV),
+                feat=torch.from_numpy(g["feat"]).to(DEV), offset=torch.from_numpy(g["offset"]).to(DEV))
+    dout = torch.from_numpy(g["dout"]).to(DEV)
+    own_pg = not dist.is_initialized()
+    if own_pg:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29547")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        model = _tiny_model(sd)
+        twin = _tiny_model(sd)                       # same parameters, takes the gradients loose
+        red = FlatGradReducer(model.parameters(), early_fraction=0.5)
+        opt, opt_twin = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.05), FusedAdamW(twin.parameters(), lr=1e-3, weight_decay=0.05)
+        for step in range(3):
+            opt.zero_grad(set_to_none=True)
+            (model(dict(data)).feat.float() * dout).sum().backward()
+            loose = [p.grad for p in model.parameters()]          # the tensors autograd produced (kept alive here)
+            red.finish()
+            for p, gl in zip(model.parameters(), loose):
+                assert p.grad.data_ptr() != gl.data_ptr() and torch.equal(p.grad, gl)     # bit-exact copy into the flat buffer
+                assert red.flat.data_ptr() <= p.grad.data_ptr() < red.flat.data_ptr() + 4 * red.flat.numel()
+            # the twin takes the same gradients loose: both optimizers must produce the same parameters, bit for bit
+            for q, gl in zip(twin.parameters(), loose):
+                q.grad = gl.clone()
+            opt.step()
+            opt_twin.step()
+            for p, q in zip(model.parameters(), twin.parameters()):
+                assert torch.equal(p, q)
+        assert red.stats == dict(steps=3, early_steps=2) and 0 < red.n_early < len(red.params)
+        assert 0.5 * red.flat.numel() <= red.early_end < red.flat.numel()
+        red.remove()
+    finally:
+        if own_pg:
+            dist.destroy_process_group()

@@ -141,6 +141,66 @@ def test_two_rank_gloo_sharding_and_reductions(tmp_path):
     assert abs(r["grad"] - 3 * (1 + 2) / 2) < 1e-6   # DDP averages gradients
 
 
+def _cpu_pack(name, grads, offs, flat):
+    """test-only packer (the product packs with one b2pc_multi_cast launch on the GPU)"""
+    for g, o in zip(grads, offs):
+        flat[o:o + g.numel()].copy_(g.reshape(-1))
+
+
+def _reducer_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from pointcept_b200.reducer import FlatGradReducer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)          # ranks start from DIFFERENT parameters: the reducer broadcasts rank 0's, like DDP
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.LayerNorm(16),
+                              torch.nn.Linear(16, 5, bias=False), torch.nn.Linear(5, 3))
+    red = FlatGradReducer(net.parameters(), early_fraction=0.5, pack=_cpu_pack)
+    import copy
+    twin = copy.deepcopy(net)        # no reducer on it: the rank-local gradients the exchange must average
+    ref = [p.detach().clone() for p in net.parameters()]
+    gathered = [torch.zeros_like(ref[0]) for _ in range(world)]
+    dist.all_gather(gathered, ref[0])
+    same_start = all(torch.equal(g, gathered[0]) for g in gathered)
+    worst, early = 0.0, []
+    for step in range(4):
+        set_none = step != 2
+        for p in net.parameters():
+            if set_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+        torch.manual_seed(100 * step + rank)
+        x = torch.randn(7 + rank, 6)      # ranks hold different batches
+        net(x).square().mean().backward()
+        local = torch.autograd.grad(twin(x).square().mean(), list(twin.parameters()))
+        red.finish()
+        early.append(red.stats["early_steps"])
+        for p, g in zip(net.parameters(), local):
+            want = g.clone()
+            dist.all_reduce(want)
+            want /= world
+            worst = max(worst, float((p.grad - want).abs().max()))
+            assert p.grad.data_ptr() >= red.flat.data_ptr() and p.grad.data_ptr() < red.flat.data_ptr() + 4 * red.flat.numel()
+    if rank == 0:
+        json.dump(dict(worst=worst, early=early, same_start=same_start, n_early=red.n_early, order=red.order), open(out, "w"))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_reducer_two_ranks_gloo(tmp_path):
+    """pointcept_b200/reducer.py (the a12 exchange): rank average of every gradient, arrival-order layout agreed across ranks,
+    early group reduced from the autograd hook, both zero_grad flavours."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r.json")
+    mp.spawn(_reducer_worker, args=(2, 29613, out), nprocs=2, join=True)
+    r = json.load(open(out))
+    assert r["same_start"]
+    assert r["worst"] < 1e-6
+    assert r["early"] == [0, 1, 2, 3]                 # first step lays the buffer out; every later step overlaps the early group
+    assert 0 < r["n_early"] < 9
+    assert r["order"][0] in (7, 8)                    # the last layer's gradients arrive first
+
+
 def test_bench_reference_arm_is_silent_on_other_ranks():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],

@@ -366,7 +366,11 @@ inline int launch_attn_fwd_umma(const void* qkv, int dtype, const int32_t* cu, i
 // The same shared-memory bytes serve as K-major operand (rows x 16 channels) and as MN-major operand (16 channels x rows):
 // only the descriptor differs.
 constexpr int kAbK = 128;   // keys per CTA (= threads)
-constexpr int kAbStages = 3;
+// Q / dO ring depth ST.  ST = 3 (round-1 order): the loads of block i+2 are issued after the wait for block i's S / dP MMAs,
+// because their stage was read by block i-1's dV / dK MMAs, which only that wait covers.  ST = 4: the stage of block i+2 was last
+// read by block i-2, complete since the previous wait, so the loads (address arithmetic, and in serialized mode the dependent
+// gidx / sidx reads, which are fetched one block further ahead into a register) are issued in the shadow of the MMA wait instead of
+// on the block's critical path.
 // BQ = queries per sweep step.  BQ = 64: 256 TMEM columns (S 64 | dP 64 | P 32 | dS 32 | dV dK dQ 48) -> 2 CTAs per SM.
 // BQ = 32: P overwrites the S columns and dS the dP columns once a thread holds its row of both in registers (TMEM lanes are
 // private to their thread), so 128 columns suffice (S/P 32 | dP/dS 32 | dV dK dQ 48) and FOUR CTAs share an SM: the kernel is
@@ -374,14 +378,14 @@ constexpr int kAbStages = 3;
 // 27 %), which twice as many resident CTAs hide.  The dQ MMA keeps M = 64 (upper 32 rows of its operand are zero planes).
 // smem: K_j 4096 | V_j 4096 | dS (A of the dQ MMA) 64x128x2 = 16384 | stages x (Q BQ*32 | dO BQ*32 | lse2 BQ*4 | delta BQ*4) | bar, slot
 template <int BQ> __host__ __device__ constexpr int attn_bwd_stage_bytes() { return BQ * 32 + BQ * 32 + BQ * 4 + BQ * 4; }
-template <int BQ> __host__ __device__ constexpr int attn_bwd_smem_bytes() { return 4096 + 4096 + 16384 + kAbStages * attn_bwd_stage_bytes<BQ>() + 64; }
+template <int BQ, int ST> __host__ __device__ constexpr int attn_bwd_smem_bytes() { return 4096 + 4096 + 16384 + ST * attn_bwd_stage_bytes<BQ>() + 64; }
 template <int BQ> __host__ __device__ constexpr int attn_bwd_tmem_cols() { return BQ == 64 ? 256 : 128; }
 
 // GATHER = true: serialized mode (see the forward kernel): qkv / dout / dqkv hold POINT rows; slot t reads point row gidx[t],
 // its dO is dout[sidx[t]] when sidx[t] >= 0 and zero otherwise (the output of a borrowed filler slot was dropped); dK / dV of a
 // primary slot go straight to the point's row of dqkv, those of filler slot with sidx = -(r+1) to row r of `side` [n_dup, 2, H, 16]
 // (added to the point's row afterwards: a point owns at most one filler slot besides its primary one).
-template <typename T, bool GATHER, int BQ>
+template <typename T, bool GATHER, int BQ, int ST>
 __global__ void __launch_bounds__(kAbK, BQ == 32 ? 4 : 2)
 attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, const float* __restrict__ lse,
                      const float* __restrict__ delta, const int32_t* __restrict__ cu, int64_t t_total, int H, float scale,
@@ -390,6 +394,8 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   using namespace umma;
   constexpr int D = 16;
   static_assert(BQ == 32 || BQ == 64, "query block");
+  static_assert(ST == 3 || ST == 4, "ring depth");
+  constexpr int kAbStages = ST;
   constexpr int kAbQ = BQ, kAbStageBytes = attn_bwd_stage_bytes<BQ>(), kAbTmemCols = attn_bwd_tmem_cols<BQ>();
   constexpr uint32_t COL_S = 0, COL_DP = BQ, COL_P = BQ == 64 ? 128 : 0, COL_DS = BQ == 64 ? 160 : BQ,
                      COL_DV = BQ == 64 ? 192 : 64, COL_DK = COL_DV + 16, COL_DQ = COL_DV + 32;
@@ -432,19 +438,25 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
     cp_async16(smem_u32(v_s + tid * 16), ok ? vs : base_k, ok);
     cp_async16(smem_u32(v_s + 2048 + tid * 16), ok ? vs + 8 : base_k, ok);
   }
-  auto load_q = [&](int blk, int stage) {
+  // row index a loading thread needs for query block blk: gidx (Q rows) for threads 0-63, sidx (dO rows, < 0 = filler slot) for
+  // threads 64-127; packed mode: the slot itself
+  auto fetch_idx = [&](int blk) -> int64_t {
+    const int which = tid >> 6, q = blk * kAbQ + (tid & 63);
+    const bool ok = (tid & 63) < kAbQ && blk < nblk && q < len;
+    if (which == 0) return ok ? (GATHER ? (int64_t)__ldg(gix + q) : (int64_t)q) : 0;
+    return ok ? (GATHER ? (int64_t)__ldg(six + q) : (int64_t)q) : -1;
+  };
+  auto load_q = [&](int blk, int stage, int64_t prow) {
     uint8_t* st = st_s + stage * kAbStageBytes;
     const int q0 = blk * kAbQ;
     if ((tid & 63) < kAbQ) {  // BQ rows x 2 chunks of Q and of dO: thread -> (which, row)
       const int which = tid >> 6, r = (tid & 63);
       const bool ok = q0 + r < len;
       if (which == 0) {
-        const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(gix + q0 + r) : 0) : (int64_t)(q0 + r);
         const T* src = base_q + prow * row_stride;
         cp_async16(smem_u32(st + r * 16), ok ? src : base_q, ok);
         cp_async16(smem_u32(st + kAbQ * 16 + r * 16), ok ? src + 8 : base_q, ok);
       } else {
-        const int64_t prow = GATHER ? (ok ? (int64_t)__ldg(six + q0 + r) : -1) : (int64_t)(q0 + r);
         const bool okd = ok && prow >= 0;
         const T* src = base_do + (okd ? prow : 0) * (H * D);
         cp_async16(smem_u32(st + kAbQ * 32 + r * 16), src, okd);
@@ -455,10 +467,11 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       cp_async4(smem_u32(st + kAbQ * 64 + which * (kAbQ * 4) + r * 4), ok ? g : base_lse, ok);
     }
   };
-  load_q(0, 0);
+  load_q(0, 0, fetch_idx(0));
   cp_async_commit();
-  if (nblk > 1) load_q(1, 1);
+  if (nblk > 1) load_q(1, 1, fetch_idx(1));
   cp_async_commit();
+  int64_t idx_next = ST == 4 ? fetch_idx(2) : 0;   // ST = 4: index of the block loaded during the next sweep step
   if (kAbQ < 64) {   // the dQ MMA has M = 64: the query rows this kernel never fills are zero planes of its A operand
     for (int q = tid; q < (64 - kAbQ) * 128 * 2 / 16; q += kAbK) reinterpret_cast<uint4*>(ds_s + kAbQ * 256)[q] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
@@ -505,10 +518,17 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       mma_ss(tmem_base + COL_DP, desc_v, make_smem_desc(smem_u32(st + kAbQ * 32), kAbQ * 16, 128), idesc_s, 0);
       mma_commit(bar);
     }
+    if (ST == 4) {   // stage (i+2)%4 was released by the previous wait: load in the shadow of this one
+      if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, idx_next);
+      cp_async_commit();
+      idx_next = fetch_idx(i + 3);
+    }
     mbar_wait(bar, i & 1);
     tc_fence_after();
-    if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages);
-    cp_async_commit();
+    if (ST == 3) {
+      if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, fetch_idx(i + 2));
+      cp_async_commit();
+    }
     if (i > 0) flush_dq(i - 1);
     const float* lse_s = reinterpret_cast<const float*>(st + kAbQ * 64);
     const float* dl_s = reinterpret_cast<const float*>(st + kAbQ * 64 + kAbQ * 4);
@@ -707,14 +727,20 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
   cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
   dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
   static const int bq = [] { const char* e = getenv("B2PC_ATTN_BQ"); return (e && atoi(e) == 64) ? 64 : 32; }();
-#define B2PC_ATTN_BWD_LAUNCH(G, Q)                                                                                                       \
+  static const int ring = [] { const char* e = getenv("B2PC_ATTN_RING"); return (e && atoi(e) == 3) ? 3 : 4; }();
+#define B2PC_ATTN_BWD_LAUNCH(G, Q, S)                                                                                                     \
   do {                                                                                                                                   \
-    cudaFuncSetAttribute(attn_bwd_umma_kernel<T, G, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes<Q>());          \
-    attn_bwd_umma_kernel<T, G, Q><<<grid, kAbK, attn_bwd_smem_bytes<Q>(), stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, t, H, \
-                                                                                   scale, (T*)dqkv, dq_acc, gidx, sidx, side);           \
+    cudaFuncSetAttribute(attn_bwd_umma_kernel<T, G, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes<Q, S>());    \
+    attn_bwd_umma_kernel<T, G, Q, S><<<grid, kAbK, attn_bwd_smem_bytes<Q, S>(), stream>>>((const T*)dout, (const T*)qkv, nlse2, delta, cu, \
+                                                                                         t, H, scale, (T*)dqkv, dq_acc, gidx, sidx, side); \
   } while (0)
-  if (gidx) { if (bq == 64) B2PC_ATTN_BWD_LAUNCH(true, 64); else B2PC_ATTN_BWD_LAUNCH(true, 32); }
-  else { if (bq == 64) B2PC_ATTN_BWD_LAUNCH(false, 64); else B2PC_ATTN_BWD_LAUNCH(false, 32); }
+  if (bq == 64) {   // round-1 tiling (2 CTAs per SM), kept for A/B
+    if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 64, 3); else B2PC_ATTN_BWD_LAUNCH(false, 64, 3);
+  } else if (ring == 3) {
+    if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 3); else B2PC_ATTN_BWD_LAUNCH(false, 32, 3);
+  } else {
+    if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 4); else B2PC_ATTN_BWD_LAUNCH(false, 32, 4);
+  }
 #undef B2PC_ATTN_BWD_LAUNCH
   attn_dq_finish_kernel<T><<<(unsigned)ceil_div(t * H, 256), 256, 0, stream>>>(dq_acc, t * H, H, scale, (T*)dqkv, sidx);
   count_launches(3);

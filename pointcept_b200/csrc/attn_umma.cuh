@@ -378,7 +378,7 @@ constexpr int kAbK = 128;   // keys per CTA (= threads)
 // 27 %), which twice as many resident CTAs hide.  The dQ MMA keeps M = 64 (upper 32 rows of its operand are zero planes).
 // smem: K_j 4096 | V_j 4096 | dS (A of the dQ MMA) 64x128x2 = 16384 | stages x (Q BQ*32 | dO BQ*32 | lse2 BQ*4 | delta BQ*4) | bar, slot
 template <int BQ> __host__ __device__ constexpr int attn_bwd_stage_bytes() { return BQ * 32 + BQ * 32 + BQ * 4 + BQ * 4; }
-template <int BQ, int ST> __host__ __device__ constexpr int attn_bwd_smem_bytes() { return 4096 + 4096 + 16384 + ST * attn_bwd_stage_bytes<BQ>() + 64; }
+template <int BQ, int ST> __host__ __device__ constexpr int attn_bwd_smem_bytes() { return 4096 + 4096 + 16384 + (ST == 3 ? 3 : 4) * attn_bwd_stage_bytes<BQ>() + 64; }
 template <int BQ> __host__ __device__ constexpr int attn_bwd_tmem_cols() { return BQ == 64 ? 256 : 128; }
 
 // GATHER = true: serialized mode (see the forward kernel): qkv / dout / dqkv hold POINT rows; slot t reads point row gidx[t],
@@ -394,8 +394,10 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   using namespace umma;
   constexpr int D = 16;
   static_assert(BQ == 32 || BQ == 64, "query block");
-  static_assert(ST == 3 || ST == 4, "ring depth");
-  constexpr int kAbStages = ST;
+  static_assert(ST == 3 || ST == 4 || ST == 5, "ring depth (5 = depth 4 with the software-pipelined MMA order)");
+  static_assert(ST != 5 || BQ == 32, "the pipelined order is written for one 32-query chunk per block");
+  constexpr bool PIPE = ST == 5;
+  constexpr int kAbStages = ST == 3 ? 3 : 4;
   constexpr int kAbQ = BQ, kAbStageBytes = attn_bwd_stage_bytes<BQ>(), kAbTmemCols = attn_bwd_tmem_cols<BQ>();
   constexpr uint32_t COL_S = 0, COL_DP = BQ, COL_P = BQ == 64 ? 128 : 0, COL_DS = BQ == 64 ? 160 : BQ,
                      COL_DV = BQ == 64 ? 192 : 64, COL_DK = COL_DV + 16, COL_DQ = COL_DV + 32;
@@ -405,7 +407,8 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   uint8_t* ds_s = smem + 8192;
   uint8_t* st_s = smem + 8192 + 16384;
   uint64_t* bar = reinterpret_cast<uint64_t*>(st_s + kAbStages * kAbStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar_b = bar + 1;                                   // pipelined order only: dQ MMAs of a block complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seq = blockIdx.y, h = blockIdx.z;
@@ -417,7 +420,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   const int64_t row_stride = (int64_t)3 * H * D;
 
   if (warp == 0) { tmem_alloc(tmem_slot, kAbTmemCols); tmem_relinquish(); }
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar_b, 1); fence_mbar_init(); }
 
   const int64_t row_base = GATHER ? 0 : s0;
   const T* base_q = qkv + (row_base * 3 + 0) * H * D + h * D;
@@ -471,7 +474,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   cp_async_commit();
   if (nblk > 1) load_q(1, 1, fetch_idx(1));
   cp_async_commit();
-  int64_t idx_next = ST == 4 ? fetch_idx(2) : 0;   // ST = 4: index of the block loaded during the next sweep step
+  int64_t idx_next = ST >= 4 ? fetch_idx(2) : 0;   // ST = 4: index of the block loaded during the next sweep step
   if (kAbQ < 64) {   // the dQ MMA has M = 64: the query rows this kernel never fills are zero planes of its A operand
     for (int q = tid; q < (64 - kAbQ) * 128 * 2 / 16; q += kAbK) reinterpret_cast<uint4*>(ds_s + kAbQ * 256)[q] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
@@ -506,30 +509,9 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
     }
   };
 
-  for (int i = 0; i < nblk; ++i) {
-    const int stage = i % kAbStages;
-    uint8_t* st = st_s + stage * kAbStageBytes;
-    cp_async_wait<1>();
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mma_ss(tmem_base + COL_S, desc_k, make_smem_desc(smem_u32(st), kAbQ * 16, 128), idesc_s, 0);
-      mma_ss(tmem_base + COL_DP, desc_v, make_smem_desc(smem_u32(st + kAbQ * 32), kAbQ * 16, 128), idesc_s, 0);
-      mma_commit(bar);
-    }
-    if (ST == 4) {   // stage (i+2)%4 was released by the previous wait: load in the shadow of this one
-      if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, idx_next);
-      cp_async_commit();
-      idx_next = fetch_idx(i + 3);
-    }
-    mbar_wait(bar, i & 1);
-    tc_fence_after();
-    if (ST == 3) {
-      if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, fetch_idx(i + 2));
-      cp_async_commit();
-    }
-    if (i > 0) flush_dq(i - 1);
+  // P^T, dS^T of one query block from S^T / dP^T in TMEM: written back to TMEM (A operands of the dV / dK MMAs) and, dS, to
+  // shared memory (A operand of the dQ MMA); pre_store() runs once before the first shared-memory store
+  auto softmax_block = [&](uint8_t* st, auto&& pre_store) {
     const float* lse_s = reinterpret_cast<const float*>(st + kAbQ * 64);
     const float* dl_s = reinterpret_cast<const float*>(st + kAbQ * 64 + kAbQ * 4);
 #pragma unroll
@@ -568,35 +550,119 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       }
       tmem_st16(lane_base + COL_P + ch * 16, pp);
       tmem_st16(lane_base + COL_DS + ch * 16, dd);
+      if (ch == 0) pre_store();   // pipelined order: the previous block's dQ MMA must be done reading ds_s
       // dS as the (MN-major) A operand of the dQ MMA: 8-query piece p of this key -> p*2048 + key*16
 #pragma unroll
       for (int pc = 0; pc < 4; ++pc)
         *reinterpret_cast<uint4*>(ds_s + (ch * 4 + pc) * 2048 + tid * 16) =
             make_uint4(dd[pc * 4], dd[pc * 4 + 1], dd[pc * 4 + 2], dd[pc * 4 + 3]);
     }
+  };
+  auto issue_sdp = [&](uint8_t* st) {      // S^T = K Q^T and dP^T = V dO^T of the query block staged at st (thread 0 only)
+    mma_ss(tmem_base + COL_S, desc_k, make_smem_desc(smem_u32(st), kAbQ * 16, 128), idesc_s, 0);
+    mma_ss(tmem_base + COL_DP, desc_v, make_smem_desc(smem_u32(st + kAbQ * 32), kAbQ * 16, 128), idesc_s, 0);
+  };
+  auto issue_dvdk = [&](uint8_t* st, bool first) {   // reduction over the BQ queries, 16 per MMA
+#pragma unroll
+    for (int ks = 0; ks < kAbQ / 16; ++ks) {
+      mma_ts(tmem_base + COL_DV, tmem_base + COL_P + ks * 8, make_smem_desc(smem_u32(st + kAbQ * 32 + ks * 256), 128, kAbQ * 16),
+             idesc_kv, (!first || ks > 0) ? 1u : 0u);
+      mma_ts(tmem_base + COL_DK, tmem_base + COL_DS + ks * 8, make_smem_desc(smem_u32(st + ks * 256), 128, kAbQ * 16), idesc_kv,
+             (!first || ks > 0) ? 1u : 0u);
+    }
+  };
+  auto issue_dq = [&]() {                   // reduction over the 128 keys
+#pragma unroll
+    for (int ks = 0; ks < kAbK / 16; ++ks)
+      mma_ss(tmem_base + COL_DQ, make_smem_desc(smem_u32(ds_s + ks * 256), 128, 2048),
+             make_smem_desc(smem_u32(k_s + ks * 256), 128, 2048), idesc_dq, ks > 0 ? 1u : 0u);
+  };
+
+  if constexpr (PIPE) {
+    // Software-pipelined order (one block barrier per query block instead of two): S / dP of block i+1 are issued right behind the
+    // dV / dK MMAs of block i, and the dQ MMA behind their commit on a second mbarrier, so the wait at the top of a block covers
+    // only what the softmax needs and the 8 dQ MMAs run under the TMEM loads and the exponentials of the next block.
+    //   barA phase k: S / dP of block k (and dV / dK of block k-1) complete;  barB phase k: dQ of block k complete.
+    cp_async_wait<1>();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_sdp(st_s);
+      mma_commit(bar);
+    }
+    for (int i = 0; i < nblk; ++i) {
+      uint8_t* st = st_s + (i % kAbStages) * kAbStageBytes;
+      if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, idx_next);   // its stage was released by the wait of block i-1
+      cp_async_commit();
+      idx_next = fetch_idx(i + 3);
+      mbar_wait(bar, i & 1);
+      tc_fence_after();
+      softmax_block(st, [&] {
+        if (i > 0) {
+          mbar_wait(bar_b, (i - 1) & 1);
+          tc_fence_after();
+          flush_dq(i - 1);
+        }
+      });
+      tmem_st_wait();
+      cp_async_wait<1>();          // block i+1 has landed (its S / dP MMAs are issued below)
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        issue_dvdk(st, i == 0);
+        if (i + 1 < nblk) issue_sdp(st_s + ((i + 1) % kAbStages) * kAbStageBytes);
+        mma_commit(bar);
+        issue_dq();
+        mma_commit(bar_b);
+      }
+    }
+    mbar_wait(bar, nblk & 1);
+    mbar_wait(bar_b, (nblk - 1) & 1);
+    tc_fence_after();
+    flush_dq(nblk - 1);
+  } else {
+  for (int i = 0; i < nblk; ++i) {
+    const int stage = i % kAbStages;
+    uint8_t* st = st_s + stage * kAbStageBytes;
+    cp_async_wait<1>();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_sdp(st);
+      mma_commit(bar);
+    }
+    if (ST == 4) {   // stage (i+2)%4 was released by the previous wait: load in the shadow of this one
+      if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, idx_next);
+      cp_async_commit();
+      idx_next = fetch_idx(i + 3);
+    }
+    mbar_wait(bar, i & 1);
+    tc_fence_after();
+    if (ST == 3) {
+      if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, fetch_idx(i + 2));
+      cp_async_commit();
+    }
+    if (i > 0) flush_dq(i - 1);
+    softmax_block(st, [] {});
     tmem_st_wait();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < kAbQ / 16; ++ks) {   // reduction over the 64 queries, 16 per MMA
-        mma_ts(tmem_base + COL_DV, tmem_base + COL_P + ks * 8, make_smem_desc(smem_u32(st + kAbQ * 32 + ks * 256), 128, kAbQ * 16),
-               idesc_kv, (i > 0 || ks > 0) ? 1u : 0u);
-        mma_ts(tmem_base + COL_DK, tmem_base + COL_DS + ks * 8, make_smem_desc(smem_u32(st + ks * 256), 128, kAbQ * 16), idesc_kv,
-               (i > 0 || ks > 0) ? 1u : 0u);
-      }
-#pragma unroll
-      for (int ks = 0; ks < kAbK / 16; ++ks)     // reduction over the 128 keys
-        mma_ss(tmem_base + COL_DQ, make_smem_desc(smem_u32(ds_s + ks * 256), 128, 2048),
-               make_smem_desc(smem_u32(k_s + ks * 256), 128, 2048), idesc_dq, ks > 0 ? 1u : 0u);
+      issue_dvdk(st, i == 0);
+      issue_dq();
       if (i == nblk - 1) mma_commit(bar);
     }
   }
   mbar_wait(bar, nblk & 1);
   tc_fence_after();
   flush_dq(nblk - 1);
+  }
   {
     uint32_t rv[16], rk[16];
     tmem_ld16(lane_base + COL_DV, rv);
@@ -727,7 +793,8 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
   cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
   dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
   static const int bq = [] { const char* e = getenv("B2PC_ATTN_BQ"); return (e && atoi(e) == 64) ? 64 : 32; }();
-  static const int ring = [] { const char* e = getenv("B2PC_ATTN_RING"); return (e && atoi(e) == 3) ? 3 : 4; }();
+  // 3: round-1 load order; 4: loads in the shadow of the MMA wait (default); 5: 4 + software-pipelined MMA order
+  static const int ring = [] { const char* e = getenv("B2PC_ATTN_RING"); const int v = e ? atoi(e) : 4; return (v == 3 || v == 5) ? v : 4; }();
 #define B2PC_ATTN_BWD_LAUNCH(G, Q, S)                                                                                                     \
   do {                                                                                                                                   \
     cudaFuncSetAttribute(attn_bwd_umma_kernel<T, G, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes<Q, S>());    \
@@ -738,6 +805,8 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
     if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 64, 3); else B2PC_ATTN_BWD_LAUNCH(false, 64, 3);
   } else if (ring == 3) {
     if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 3); else B2PC_ATTN_BWD_LAUNCH(false, 32, 3);
+  } else if (ring == 5) {
+    if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 5); else B2PC_ATTN_BWD_LAUNCH(false, 32, 5);
   } else {
     if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 4); else B2PC_ATTN_BWD_LAUNCH(false, 32, 4);
   }

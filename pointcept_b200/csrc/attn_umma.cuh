@@ -394,9 +394,14 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   using namespace umma;
   constexpr int D = 16;
   static_assert(BQ == 32 || BQ == 64, "query block");
-  static_assert(ST == 3 || ST == 4 || ST == 5, "ring depth (5 = depth 4 with the software-pipelined MMA order)");
-  static_assert(ST != 5 || BQ == 32, "the pipelined order is written for one 32-query chunk per block");
+  static_assert(ST >= 3 && ST <= 6, "3 / 4: ring depth; 5: depth 4 + software-pipelined MMA order; 6: depth 4 + paired dQ MMA");
+  static_assert(ST < 5 || BQ == 32, "modes 5 and 6 are written for one 32-query chunk per block");
   constexpr bool PIPE = ST == 5;
+  // PAIR: the dQ MMA has M = 64 but a block brings 32 queries, so half of every dQ MMA multiplies zero planes.  Two consecutive
+  // blocks write their dS into the lower / upper four planes of the operand and the 8 dQ MMAs are issued once per pair: 10 instead
+  // of 14 tcgen05.mma per block (ncu: the TC pipe is busy 55 % of the time at ~36 cycles per instruction, whatever its N).
+  constexpr bool PAIR = ST == 6;
+  constexpr bool EARLY = ST == 4 || ST == 6;   // loads of block i+2 in the shadow of the MMA wait
   constexpr int kAbStages = ST == 3 ? 3 : 4;
   constexpr int kAbQ = BQ, kAbStageBytes = attn_bwd_stage_bytes<BQ>(), kAbTmemCols = attn_bwd_tmem_cols<BQ>();
   constexpr uint32_t COL_S = 0, COL_DP = BQ, COL_P = BQ == 64 ? 128 : 0, COL_DS = BQ == 64 ? 160 : BQ,
@@ -474,7 +479,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   cp_async_commit();
   if (nblk > 1) load_q(1, 1, fetch_idx(1));
   cp_async_commit();
-  int64_t idx_next = ST >= 4 ? fetch_idx(2) : 0;   // ST = 4: index of the block loaded during the next sweep step
+  int64_t idx_next = ST >= 4 ? fetch_idx(2) : 0;   // modes 4-6   // ST = 4: index of the block loaded during the next sweep step
   if (kAbQ < 64) {   // the dQ MMA has M = 64: the query rows this kernel never fills are zero planes of its A operand
     for (int q = tid; q < (64 - kAbQ) * 128 * 2 / 16; q += kAbK) reinterpret_cast<uint4*>(ds_s + kAbQ * 256)[q] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
@@ -495,12 +500,14 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
   const uint64_t c2 = pack_f2(c, c);
 
   auto flush_dq = [&](int blk) {
-    // dQ partial of query block blk: M=64 accumulator, row r lives in lane (r%16) + 32*(r/16); 16 fp32 columns
+    // dQ partial of query block blk (PAIR: of the two blocks 2*blk, 2*blk+1): M=64 accumulator, row r lives in lane
+    // (r%16) + 32*(r/16); 16 fp32 columns
+    constexpr int kRows = PAIR ? 64 : kAbQ;
     uint32_t r[16];
     tmem_ld16(lane_base + COL_DQ, r);
     tmem_ld_wait();
-    const int qi = blk * kAbQ + warp * 16 + lane;
-    if (lane < 16 && warp * 16 < kAbQ && qi < len) {
+    const int qi = blk * kRows + warp * 16 + lane;
+    if (lane < 16 && warp * 16 < kRows && qi < len) {
       float* dst = dq_acc + ((s0 + qi) * H + h) * D;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -511,7 +518,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
 
   // P^T, dS^T of one query block from S^T / dP^T in TMEM: written back to TMEM (A operands of the dV / dK MMAs) and, dS, to
   // shared memory (A operand of the dQ MMA); pre_store() runs once before the first shared-memory store
-  auto softmax_block = [&](uint8_t* st, auto&& pre_store) {
+  auto softmax_block = [&](uint8_t* st, int plane0, auto&& pre_store) {
     const float* lse_s = reinterpret_cast<const float*>(st + kAbQ * 64);
     const float* dl_s = reinterpret_cast<const float*>(st + kAbQ * 64 + kAbQ * 4);
 #pragma unroll
@@ -554,7 +561,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       // dS as the (MN-major) A operand of the dQ MMA: 8-query piece p of this key -> p*2048 + key*16
 #pragma unroll
       for (int pc = 0; pc < 4; ++pc)
-        *reinterpret_cast<uint4*>(ds_s + (ch * 4 + pc) * 2048 + tid * 16) =
+        *reinterpret_cast<uint4*>(ds_s + (plane0 + ch * 4 + pc) * 2048 + tid * 16) =
             make_uint4(dd[pc * 4], dd[pc * 4 + 1], dd[pc * 4 + 2], dd[pc * 4 + 3]);
     }
   };
@@ -598,7 +605,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       idx_next = fetch_idx(i + 3);
       mbar_wait(bar, i & 1);
       tc_fence_after();
-      softmax_block(st, [&] {
+      softmax_block(st, 0, [&] {
         if (i > 0) {
           mbar_wait(bar_b, (i - 1) & 1);
           tc_fence_after();
@@ -635,7 +642,7 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       issue_sdp(st);
       mma_commit(bar);
     }
-    if (ST == 4) {   // stage (i+2)%4 was released by the previous wait: load in the shadow of this one
+    if (EARLY) {   // stage (i+2)%4 was released by the previous wait: load in the shadow of this one
       if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, idx_next);
       cp_async_commit();
       idx_next = fetch_idx(i + 3);
@@ -646,8 +653,12 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
       if (i + 2 < nblk) load_q(i + 2, (i + 2) % kAbStages, fetch_idx(i + 2));
       cp_async_commit();
     }
-    if (i > 0) flush_dq(i - 1);
-    softmax_block(st, [] {});
+    if (PAIR) {
+      if (i > 0 && ((i - 1) & 1)) flush_dq((i - 1) >> 1);     // the pair that ended with block i-1
+    } else if (i > 0) {
+      flush_dq(i - 1);
+    }
+    softmax_block(st, PAIR ? (i & 1) * 4 : 0, [] {});
     tmem_st_wait();
     fence_proxy_async();
     tc_fence_before();
@@ -655,13 +666,13 @@ attn_bwd_umma_kernel(const T* __restrict__ dout, const T* __restrict__ qkv, cons
     if (tid == 0) {
       tc_fence_after();
       issue_dvdk(st, i == 0);
-      issue_dq();
+      if (!PAIR || (i & 1) || i == nblk - 1) issue_dq();
       if (i == nblk - 1) mma_commit(bar);
     }
   }
   mbar_wait(bar, nblk & 1);
   tc_fence_after();
-  flush_dq(nblk - 1);
+  flush_dq(PAIR ? (nblk - 1) >> 1 : nblk - 1);
   }
   {
     uint32_t rv[16], rk[16];
@@ -793,8 +804,9 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
   cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
   dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
   static const int bq = [] { const char* e = getenv("B2PC_ATTN_BQ"); return (e && atoi(e) == 64) ? 64 : 32; }();
-  // 3: round-1 load order; 4: loads in the shadow of the MMA wait (default); 5: 4 + software-pipelined MMA order
-  static const int ring = [] { const char* e = getenv("B2PC_ATTN_RING"); const int v = e ? atoi(e) : 4; return (v == 3 || v == 5) ? v : 4; }();
+  // 3: round-1 load order; 4: loads in the shadow of the MMA wait (default); 5: 4 + software-pipelined MMA order (parity-green,
+  // slower on B200: 0.433 vs 0.417 ms); 6: 4 + one dQ MMA burst per pair of query blocks
+  static const int ring = [] { const char* e = getenv("B2PC_ATTN_RING"); const int v = e ? atoi(e) : 4; return (v == 3 || v == 5 || v == 6) ? v : 4; }();
 #define B2PC_ATTN_BWD_LAUNCH(G, Q, S)                                                                                                     \
   do {                                                                                                                                   \
     cudaFuncSetAttribute(attn_bwd_umma_kernel<T, G, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes<Q, S>());    \
@@ -807,6 +819,8 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
     if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 3); else B2PC_ATTN_BWD_LAUNCH(false, 32, 3);
   } else if (ring == 5) {
     if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 5); else B2PC_ATTN_BWD_LAUNCH(false, 32, 5);
+  } else if (ring == 6) {
+    if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 6); else B2PC_ATTN_BWD_LAUNCH(false, 32, 6);
   } else {
     if (gidx) B2PC_ATTN_BWD_LAUNCH(true, 32, 4); else B2PC_ATTN_BWD_LAUNCH(false, 32, 4);
   }

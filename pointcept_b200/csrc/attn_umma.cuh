@@ -804,9 +804,10 @@ inline int launch_attn_bwd_umma_t(const void* dout, const void* qkv, const void*
   cudaMemsetAsync(dq_acc, 0, (size_t)t * H * 16 * sizeof(float), stream);
   dim3 grid((unsigned)ceil_div(max_seqlen, kAbK), n_seq, H);
   static const int bq = [] { const char* e = getenv("B2PC_ATTN_BQ"); return (e && atoi(e) == 64) ? 64 : 32; }();
-  // 3: round-1 load order; 4: loads in the shadow of the MMA wait (default); 5: 4 + software-pipelined MMA order (parity-green,
-  // slower on B200: 0.433 vs 0.417 ms); 6: 4 + one dQ MMA burst per pair of query blocks
-  static const int ring = [] { const char* e = getenv("B2PC_ATTN_RING"); const int v = e ? atoi(e) : 4; return (v == 3 || v == 5 || v == 6) ? v : 4; }();
+  // B2PC_ATTN_RING, measured on B200 at H = 2, T = 241 664, K = 1024 (profiles/r02_attn_bwd_ring_ab.txt):
+  //   3: round-1 load order (0.441 ms); 4: loads in the shadow of the MMA wait (0.415 ms); 5: 4 + software-pipelined MMA order
+  //   (0.433 ms: the block barrier was not the limiter); 6 (default): 4 + one dQ MMA burst per pair of query blocks (0.388 ms)
+  static const int ring = [] { const char* e = getenv("B2PC_ATTN_RING"); const int v = e ? atoi(e) : 6; return (v == 3 || v == 4 || v == 5) ? v : 6; }();
 #define B2PC_ATTN_BWD_LAUNCH(G, Q, S)                                                                                                     \
   do {                                                                                                                                   \
     cudaFuncSetAttribute(attn_bwd_umma_kernel<T, G, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes<Q, S>());    \

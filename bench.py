@@ -513,7 +513,7 @@ def run_ours(args):
 
     # ---- supplementary, driver-visible lines for the other BASELINE configs (short runs; same contract: warm-up >= 3, events) ----
     supp = {}
-    if not args.no_supplementary:
+    if not args.no_supplementary and world == 1:   # single-GPU lines (per-GPU shapes of configs 3 and 5); N > 1 runs measure scaling
         try:
             other = "spunet34" if args.workload == "ptv3_base" else "ptv3_base"
             r = measure(args, other, 8 if other == "spunet34" else 2, args.voxels, 10, 3, want_e2e=False)

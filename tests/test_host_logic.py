@@ -201,6 +201,51 @@ def test_flat_grad_reducer_two_ranks_gloo(tmp_path):
     assert r["order"][0] in (7, 8)                    # the last layer's gradients arrive first
 
 
+def test_flat_grad_reducer_single_rank_edge_cases():
+    """world size 1 (gloo, in-process): no early group when early_fraction = 0, loud errors for an unused parameter, hooks removed."""
+    import torch.distributed as dist
+    from pointcept_b200.reducer import FlatGradReducer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29619")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2))
+        red = FlatGradReducer(net.parameters(), early_fraction=0.0, pack=_cpu_pack)
+        for _ in range(3):
+            for p in net.parameters():
+                p.grad = None
+            x = torch.randn(5, 4)
+            net(x).sum().backward()
+            want = [p.grad.clone() for p in net.parameters()]
+            red.finish()
+            assert all(torch.equal(p.grad, w) for p, w in zip(net.parameters(), want))
+        assert red.stats == dict(steps=3, early_steps=0) and red.n_early == 0
+        assert red.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in net.parameters())      # 16-byte aligned slices
+        red.enabled = False            # gradient accumulation micro-steps: the reducer stays out of the way
+        net(torch.randn(5, 4)).sum().backward()
+        red.finish()
+        assert red.stats["steps"] == 3
+        red.remove()
+        # a parameter that takes no part in the loss: refused on the first step, like DDP(find_unused_parameters=False)
+        unused = torch.nn.Linear(3, 3)
+        red2 = FlatGradReducer(list(net.parameters()) + list(unused.parameters()), pack=_cpu_pack)
+        for p in net.parameters():
+            p.grad = None
+        net(torch.randn(5, 4)).sum().backward()
+        with pytest.raises(RuntimeError, match="received no gradient"):
+            red2.finish()
+        red2.remove()
+        with pytest.raises(RuntimeError, match="GPU only"):                 # the product packer has no CPU path
+            red3 = FlatGradReducer(net.parameters())
+            for p in net.parameters():
+                p.grad = None
+            net(torch.randn(5, 4)).sum().backward()
+            red3.finish()
+        red3.remove()
+    finally:
+        dist.destroy_process_group()
+
+
 def test_bench_reference_arm_is_silent_on_other_ranks():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],

@@ -401,7 +401,7 @@ def measure(args, workload, scenes, voxels, steps, warmup, kind="indoor", want_p
             res["e2e_value"] = total_points * steps / dt
             res["loss_last"] = float(loss_pinned[-1])
     if reducer is not None:
-        res["grad_exchange"] = dict(kind="flat", steps=reducer.stats["steps"], overlapped_steps=reducer.stats["early_steps"],
+        res["grad_exchange"] = dict(kind="flat", steps=reducer.stats["steps"], overlapped_steps=reducer.stats["early_steps"], late_steps=reducer.stats["late_steps"],
                                     early_bytes=4 * reducer.early_end, total_bytes=4 * reducer.flat.numel())
         reducer.remove()
     elif dist_on and not reference_stack:

@@ -101,7 +101,7 @@ class FlatGradReducer:
         self._early_work = None
         self._early_done = False
         self.enabled = True
-        self.stats = dict(steps=0, early_steps=0)
+        self.stats = dict(steps=0, early_steps=0, late_steps=0)
         if broadcast:
             with torch.no_grad():
                 for p in self.params:
@@ -165,13 +165,18 @@ class FlatGradReducer:
     def _early_hook(self, _p):
         if not self.enabled or self._early_done or self.order is None:
             return
+        if any(self.params[i].grad is None for i in self.order[:self.n_early]):
+            return      # this rank's backward pass ran in another order: finish() issues the same collective, just not overlapped
         self._pack_group("early", self.order[:self.n_early])
         self._early_work, self._early_div = self._all_reduce(self.flat[:self.early_end], True)
         self._early_done = True
+        self.stats["early_steps"] += 1
 
     @torch.no_grad()
     def finish(self):
-        """Call after ``loss.backward()``: afterwards every ``p.grad`` is its slice of the flat buffer holding the rank average."""
+        """Call after ``loss.backward()``: afterwards every ``p.grad`` is its slice of the flat buffer holding the rank average.
+        Every rank issues the same collectives in the same order on every step (layout step: broadcast + one all-reduce; afterwards
+        the early slice, then the rest) whether or not its own trigger fired, so ranks can never disagree on the sequence."""
         if not self.enabled:
             return
         self.stats["steps"] += 1
@@ -183,12 +188,13 @@ class FlatGradReducer:
             if div:
                 self.flat.div_(self.world)
         else:
-            if self._early_done:
-                rest, lo = self.order[self.n_early:], self.early_end
-                self.stats["early_steps"] += 1
-            else:                                                # no trigger (early_fraction = 0 or a one-parameter model)
-                rest, lo = self.order, 0
-            self._pack_group("rest" if lo else "all", rest)
+            lo = self.early_end if self.n_early > 0 else 0
+            if self.n_early > 0 and not self._early_done:        # trigger did not fire / found a gradient missing: same collective, late
+                self._pack_group("early", self.order[:self.n_early])
+                self._early_work, self._early_div = self._all_reduce(self.flat[:lo], True)
+                self._early_done = True
+                self.stats["late_steps"] += 1
+            self._pack_group("rest" if lo else "all", self.order[self.n_early:])
             _, div = self._all_reduce(self.flat[lo:], False)
             if div:
                 self.flat[lo:].div_(self.world)

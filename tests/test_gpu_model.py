@@ -436,7 +436,7 @@ def test_flat_grad_reducer_nccl_packs_bit_exact_and_feeds_fused_adamw(golden_dir
             opt_twin.step()
             for p, q in zip(model.parameters(), twin.parameters()):
                 assert torch.equal(p, q)
-        assert red.stats == dict(steps=3, early_steps=2) and 0 < red.n_early < len(red.params)
+        assert red.stats == dict(steps=3, early_steps=2, late_steps=0) and 0 < red.n_early < len(red.params)
         assert 0.5 * red.flat.numel() <= red.early_end < red.flat.numel()
         red.remove()
     finally:

@@ -163,8 +163,10 @@ def _reducer_worker(rank, world, port, out):
     dist.all_gather(gathered, ref[0])
     same_start = all(torch.equal(g, gathered[0]) for g in gathered)
     worst, early = 0.0, []
-    for step in range(4):
+    for step in range(5):
         set_none = step != 2
+        if step == 4 and rank == 1:      # this rank's trigger never fires: it must still issue the same collectives (late), no hang
+            red._trigger_handle.remove()
         for p in net.parameters():
             if set_none:
                 p.grad = None
@@ -183,7 +185,9 @@ def _reducer_worker(rank, world, port, out):
             worst = max(worst, float((p.grad - want).abs().max()))
             assert p.grad.data_ptr() >= red.flat.data_ptr() and p.grad.data_ptr() < red.flat.data_ptr() + 4 * red.flat.numel()
     if rank == 0:
-        json.dump(dict(worst=worst, early=early, same_start=same_start, n_early=red.n_early, order=red.order), open(out, "w"))
+        json.dump(dict(worst=worst, early=early, same_start=same_start, n_early=red.n_early, order=red.order, stats=red.stats), open(out, "w"))
+    else:
+        assert red.stats == dict(steps=5, early_steps=3, late_steps=1)
     dist.destroy_process_group()
 
 
@@ -196,7 +200,8 @@ def test_flat_grad_reducer_two_ranks_gloo(tmp_path):
     r = json.load(open(out))
     assert r["same_start"]
     assert r["worst"] < 1e-6
-    assert r["early"] == [0, 1, 2, 3]                 # first step lays the buffer out; every later step overlaps the early group
+    assert r["early"] == [0, 1, 2, 3, 4]              # first step lays the buffer out; every later step overlaps the early group
+    assert r["stats"] == dict(steps=5, early_steps=4, late_steps=0)   # (rank 1 ran its last step late: asserted in the worker)
     assert 0 < r["n_early"] < 9
     assert r["order"][0] in (7, 8)                    # the last layer's gradients arrive first
 
@@ -219,7 +224,7 @@ def test_flat_grad_reducer_single_rank_edge_cases():
             want = [p.grad.clone() for p in net.parameters()]
             red.finish()
             assert all(torch.equal(p.grad, w) for p, w in zip(net.parameters(), want))
-        assert red.stats == dict(steps=3, early_steps=0) and red.n_early == 0
+        assert red.stats == dict(steps=3, early_steps=0, late_steps=0) and red.n_early == 0
         assert red.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in net.parameters())      # 16-byte aligned slices
         red.enabled = False            # gradient accumulation micro-steps: the reducer stays out of the way
         net(torch.randn(5, 4)).sum().backward()

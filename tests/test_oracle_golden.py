@@ -111,3 +111,27 @@ def test_point_rope_oracle_matches_reference_fixture(golden_dir):
         # rotation by the negative angle is the inverse (what PointROPE_func.backward applies, litept_v1.py:40-46)
         back = oev.point_rope(y, torch.from_numpy(g[name + "_pos"]), float(g[name + "_base"]), -1.0)
         assert float((back - torch.from_numpy(g[name + "_tokens"])).abs().max()) <= 1e-5
+
+
+def test_knn_oracle_corroborated_by_scipy_ckdtree():
+    """The reference's knn_query is CUDA-only (libs/pointops/src/knn_query) and ships no vectors, so oracle/eval_ops.knn_query cannot be
+    pinned; it is checked here against an independent exact k-NN (scipy's cKDTree): per-scene search, ascending order, global row
+    indices, Euclidean distance, and the -1 / 1e5 placeholders when a scene holds fewer than k points."""
+    import numpy as np
+    from scipy.spatial import cKDTree
+    from oracle import eval_ops
+    rng = np.random.default_rng(5)
+    sizes, qsizes, k = [300, 7, 120], [40, 5, 33], 9
+    xyz = rng.uniform(-2, 2, (sum(sizes), 3)).astype(np.float32)
+    new = rng.uniform(-2, 2, (sum(qsizes), 3)).astype(np.float32)
+    offset, new_offset = np.cumsum(sizes), np.cumsum(qsizes)
+    idx, dist = eval_ops.knn_query(k, xyz, offset, new, new_offset)
+    s = qs = 0
+    for e, qe in zip(offset, new_offset):
+        kk = min(k, e - s)
+        d_ref, i_ref = cKDTree(xyz[s:e].astype(np.float64)).query(new[qs:qe].astype(np.float64), k=kk)
+        d_ref, i_ref = d_ref.reshape(qe - qs, kk), i_ref.reshape(qe - qs, kk)
+        assert np.array_equal(idx[qs:qe, :kk], i_ref + s)                    # same neighbours, same (ascending) order, global rows
+        assert np.allclose(dist[qs:qe, :kk], d_ref, rtol=0, atol=2e-6)
+        assert (idx[qs:qe, kk:] == -1).all() and np.allclose(dist[qs:qe, kk:], 1e5)      # sqrt(1e10) placeholders
+        s, qs = e, qe

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from oracle import ptv3_cpu
+from oracle import spunet_cpu
 from oracle import spconv_ref as osp
 from pointcept_b200 import ops, synth
 from pointcept_b200.ptv3 import PointTransformerV3
@@ -192,58 +193,8 @@ def test_spunet_forward_backward_vs_oracle_convs():
     out.square().mean().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
     # oracle replay of the same network on CPU
-    ref = _spunet_cpu({k: v.detach().cpu() for k, v in model.state_dict().items()}, b, model)
+    ref = spunet_cpu.forward({k: v.detach().cpu() for k, v in model.state_dict().items()}, b, model)
     assert rel_l2(out.detach(), ref) < 1e-3
-
-
-def _spunet_cpu(sd, b, model):
-    import torch.nn.functional as F
-    bid = np.repeat(np.arange(len(b["offset"])), np.diff(b["offset"], prepend=0))
-    idx = np.concatenate([bid[:, None], b["grid_coord"]], 1).astype(np.int32)
-    shape = (b["grid_coord"].max(0) + 96).tolist()
-
-    def bn(x, p):
-        return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.0, 1e-3)
-
-    def w(p):
-        t = sd[p + ".weight"]
-        return t.reshape(t.shape[0], -1, t.shape[-1])
-
-    books = {}
-
-    def subm(x, p, key, ks):
-        if (key, ks) not in books:
-            books[(key, ks)] = osp.subm_rulebook(levels[key][0], levels[key][1], ks)
-        return osp.conv_apply(x, w(p), books[(key, ks)], sd.get(p + ".bias"))
-
-    def block(x, p, key):
-        res = x
-        if p + ".proj.0.weight" in sd:
-            res = bn(F.linear(x, w(p + ".proj.0")[:, 0, :]), p + ".proj.1")
-        y = F.relu(bn(subm(x, p + ".conv1", key, 3), p + ".bn1"))
-        y = bn(subm(y, p + ".conv2", key, 3), p + ".bn2")
-        return F.relu(y + res)
-
-    levels = {0: (idx, shape)}
-    x = torch.from_numpy(b["feat"])
-    x = F.relu(bn(subm(x, "conv_input.0", 0, 5), "conv_input.1"))
-    skips, strided = [x], {}
-    ns = model.num_stages
-    for s in range(ns):
-        oi, osh, pf, pb = osp.strided_rulebook(levels[s][0], levels[s][1], 2, 2)
-        strided[s] = (pf, pb)
-        levels[s + 1] = (oi, osh)
-        x = F.relu(bn(osp.conv_apply(x, w(f"down.{s}.0"), pf), f"down.{s}.1"))
-        for i in range(model.layers[s]):
-            x = block(x, f"enc.{s}.block{i}", s + 1)
-        skips.append(x)
-    x = skips.pop(-1)
-    for s in reversed(range(ns)):
-        x = F.relu(bn(osp.inverse_conv_apply(x, w(f"up.{s}.0"), strided[s][1]), f"up.{s}.1"))
-        x = torch.cat([x, skips.pop(-1)], 1)
-        for i in range(model.layers[len(model.channels) - s - 1]):
-            x = block(x, f"dec.{s}.block{i}", s)
-    return F.linear(x, w("final")[:, 0, :], sd["final.bias"])
 
 
 # ---- BASELINE.json configs 3 and 5 at full scene size: size-independent properties -------------------------------------------

@@ -261,6 +261,37 @@ def gen_point_rope():
     print("point_rope.npz", {k: v.shape for k, v in out.items() if k.endswith("_out")})
 
 
+def gen_spunet_tiny():
+    """The UNMODIFIED reference SpUNet-v1m1 (spconv_unet_v1m1_base.py:88-280) run on CPU in training mode, with spconv stood in by
+    oracle/spconv_ref.py (SubMConv3d k5 / k3 / k1, SparseConv3d k2 s2, SparseInverseConv3d k2, SparseSequential dispatch).  Pins the
+    model-level restatement oracle/spunet_cpu.py (block structure, BatchNorm eps, skip concatenation order, indice_key pairing)."""
+    ref = ref_import.load_models(use_shims="oracle")
+    from pointcept_b200 import synth
+    torch.manual_seed(5)
+    cfg = dict(in_channels=6, num_classes=13, base_channels=8, channels=(8, 16, 16, 24, 24, 16, 16, 8), layers=(2, 1, 1, 1, 1, 1, 1, 2))
+    model = ref.spunet.SpUNetBase(**cfg)
+    model.train()
+    with torch.no_grad():        # the reference initialises BatchNorm to (1, 0) and biases to 0: perturb so that every term is exercised
+        for k, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    b = synth.make_batch(2, seed=21, target_voxels=1200)
+    out = model(dict(grid_coord=torch.from_numpy(b["grid_coord"]), feat=torch.from_numpy(b["feat"]), offset=torch.from_numpy(b["offset"])))
+    g = torch.randn_like(out)
+    out.backward(g)
+    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    grads = {"grad::" + k: p.grad.numpy() for k, p in model.named_parameters()}
+    np.savez_compressed(os.path.join(OUT, "spunet_tiny.npz"), grid_coord=b["grid_coord"], offset=b["offset"], feat=b["feat"],
+                        out=out.detach().numpy(), dout=g.numpy(), layers=np.array(cfg["layers"]), channels=np.array(cfg["channels"]),
+                        **{"sd::" + k: v for k, v in sd.items()}, **grads)
+    print("spunet_tiny.npz", out.shape, float(out.abs().mean()), len(grads), "parameter gradients")
+
+
+if __name__ == "__main__" and "--only-spunet" in sys.argv:
+    assert ref_import.available(), "needs /root/reference"
+    gen_spunet_tiny()
+    sys.exit(0)
+
 if __name__ == "__main__" and "--only-rope" in sys.argv:
     assert ref_import.available(), "needs /root/reference"
     gen_point_rope()
@@ -282,5 +313,6 @@ if __name__ == "__main__":
         gen_point_and_padding()
         gen_grid_sample()
         gen_point_rope()
+        gen_spunet_tiny()
         gen_ptv3_tiny()
 

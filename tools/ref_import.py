@@ -95,9 +95,68 @@ def _install_oracle_spconv():
             w = self.weight.reshape(self.weight.shape[0], -1, self.weight.shape[-1])
             return x.replace_feature(osp.conv_apply(x.features, w, pair, self.bias))
 
+    class SparseConv3d(SparseModule):
+        """strided sparse conv on the oracle rulebook; remembers, under its indice_key, what SparseInverseConv3d needs"""
+        def __init__(self, cin, cout, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True, indice_key=None, **kw):
+            super().__init__()
+            self.k, self.s, self.p, self.indice_key = kernel_size, stride, padding, indice_key
+            self.weight = nn.Parameter(torch.empty(cout, kernel_size, kernel_size, kernel_size, cin))
+            self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+            nn.init.normal_(self.weight, std=0.05)
+
+        def forward(self, x):
+            oi, osh, pf, pb = osp.strided_rulebook(x.indices.numpy(), x.spatial_shape, self.k, self.s, self.p)
+            if self.indice_key is not None:
+                x.indice_dict[("strided", self.indice_key)] = (x.indices, x.spatial_shape, pb)
+            w = self.weight.reshape(self.weight.shape[0], -1, self.weight.shape[-1])
+            return SparseConvTensor(osp.conv_apply(x.features, w, pf, self.bias), torch.from_numpy(oi), osh, x.batch_size, x.indice_dict)
+
+    class SparseInverseConv3d(SparseModule):
+        def __init__(self, cin, cout, kernel_size, indice_key=None, bias=True, **kw):
+            super().__init__()
+            self.k, self.indice_key = kernel_size, indice_key
+            self.weight = nn.Parameter(torch.empty(cout, kernel_size, kernel_size, kernel_size, cin))
+            self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+            nn.init.normal_(self.weight, std=0.05)
+
+        def forward(self, x):
+            indices, shape, pb = x.indice_dict[("strided", self.indice_key)]
+            w = self.weight.reshape(self.weight.shape[0], -1, self.weight.shape[-1])
+            return SparseConvTensor(osp.inverse_conv_apply(x.features, w, pb, self.bias), indices, shape, x.batch_size, x.indice_dict)
+
+    class SparseSequential(SparseModule):
+        """spconv's container: sparse modules take the tensor, plain modules (BatchNorm1d, ReLU, Identity) its features"""
+        def __init__(self, *args, **kwargs):
+            super().__init__()
+            import collections
+            if len(args) == 1 and isinstance(args[0], collections.OrderedDict):
+                for k, m in args[0].items():
+                    self.add_module(k, m)
+            else:
+                for i, m in enumerate(args):
+                    self.add_module(str(i), m)
+            for k, m in kwargs.items():
+                self.add_module(k, m)
+
+        def __getitem__(self, i):
+            return list(self._modules.values())[i]
+
+        def __len__(self):
+            return len(self._modules)
+
+        def forward(self, x):
+            for m in self._modules.values():
+                if isinstance(m, SparseModule):
+                    x = m(x)
+                elif isinstance(x, SparseConvTensor):
+                    x = x.replace_feature(m(x.features))
+                else:
+                    x = m(x)
+            return x
+
     sp = _mod("spconv")
-    spt = _mod("spconv.pytorch", SubMConv3d=SubMConv3d, SparseConv3d=None, SparseInverseConv3d=None,
-               SparseModule=SparseModule, SparseSequential=nn.Sequential, Identity=nn.Identity,
+    spt = _mod("spconv.pytorch", SubMConv3d=SubMConv3d, SparseConv3d=SparseConv3d, SparseInverseConv3d=SparseInverseConv3d,
+               SparseModule=SparseModule, SparseSequential=SparseSequential, Identity=nn.Identity,
                SparseConvTensor=SparseConvTensor)
     spt.modules = _mod("spconv.pytorch.modules", is_spconv_module=lambda m: isinstance(m, SparseModule))
     sp.pytorch = spt

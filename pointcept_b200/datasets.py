@@ -52,6 +52,8 @@ def collate_fn(batch):
         return torch.cat(list(batch))
     if isinstance(first, str):
         return list(batch)
+    if isinstance(first, list):                      # python lists of numbers (utils.py:32-34)
+        return torch.cat([torch.tensor(d) for d in batch])
     if isinstance(first, Mapping):
         out = {}
         for key in first:
@@ -65,8 +67,11 @@ def collate_fn(batch):
             sizes = torch.tensor([d["coord"].shape[0] for d in batch], dtype=torch.int64)
             out["offset"] = torch.cumsum(sizes, 0).to(first["coord"].device)
         return out
-    if isinstance(first, Sequence):
-        return [collate_fn(list(s)) for s in zip(*batch)]
+    if isinstance(first, Sequence):                  # tuples of per-point tensors: the reference appends the cumulative offset
+        cols = [collate_fn(list(s)) for s in zip(*batch)]         # (int32, from the first entry's lengths) as the last item (utils.py:35-40)
+        sizes = torch.tensor([d[0].shape[0] for d in batch], dtype=torch.int64, device=cols[0].device)
+        cols.append(torch.cumsum(sizes, dim=0).int())
+        return cols
     return torch.utils.data.dataloader.default_collate(batch)
 
 

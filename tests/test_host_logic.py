@@ -291,3 +291,68 @@ def test_non_flash_rpe_attention_branch_matches_reference_fixture(golden_dir):
     assert torch.allclose(out.detach(), torch.from_numpy(g["out"]), rtol=1e-5, atol=1e-6)
     assert torch.allclose(feat.grad, torch.from_numpy(g["dfeat"]), rtol=1e-4, atol=1e-6)
     assert torch.allclose(attn.rpe.rpe_table.grad, torch.from_numpy(g["d_rpe_table"]), rtol=1e-4, atol=1e-6)
+
+
+def test_collate_fn_matches_the_reference_function():
+    """pointcept_b200.datasets.collate_fn vs the reference's own collate_fn (pointcept/datasets/utils.py:19-73) on CPU tensors: dicts with
+    per-sample offsets (what Collect emits), bare tensors, tuples of tensors (offset appended), lists of numbers, strings."""
+    if not ref_import.available():
+        pytest.skip("needs /root/reference")
+    import importlib.util
+    import types
+    from pointcept_b200 import datasets
+    saved = {k: sys.modules.get(k) for k in ("torch_scatter", "pointcept", "pointcept.models", "pointcept.models.utils")}
+    try:
+        sys.modules["torch_scatter"] = types.SimpleNamespace(scatter_min=None)
+        for name in ("pointcept", "pointcept.models"):
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["pointcept.models.utils"] = types.SimpleNamespace(offset2batch=None)
+        spec = importlib.util.spec_from_file_location("_ref_datasets_utils", os.path.join(ref_import.REF, "pointcept/datasets/utils.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    g = torch.Generator().manual_seed(0)
+
+    def sample(n, with_offset=True):
+        d = dict(coord=torch.randn(n, 3, generator=g), grid_coord=torch.randint(0, 50, (n, 3), generator=g),
+                 segment=torch.randint(0, 20, (n,), generator=g), name="scene%d" % n)
+        if with_offset:
+            d["offset"] = torch.tensor([n])
+        return d
+
+    def same(a, b):
+        if isinstance(a, torch.Tensor):
+            assert isinstance(b, torch.Tensor) and a.dtype == b.dtype and torch.equal(a, b)
+        elif isinstance(a, dict):
+            assert a.keys() == b.keys()
+            for k in a:
+                same(a[k], b[k])
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                same(x, y)
+        else:
+            assert a == b
+
+    batch = [sample(5), sample(9), sample(1)]
+    same(ref.collate_fn([dict(d) for d in batch]), datasets.collate_fn([dict(d) for d in batch]))
+    # a fragment list: per-sample offsets that already hold several scenes (test-time fragments are collated twice, test.py:170-176)
+    strip = lambda d: {k: v for k, v in d.items() if k != "name"}     # noqa: E731  (the reference cannot re-collate lists of str)
+    two = [ref.collate_fn([strip(d) for d in batch[:2]]), ref.collate_fn([strip(d) for d in batch[1:]])]
+    same(ref.collate_fn([dict(d) for d in two]), datasets.collate_fn([dict(d) for d in two]))
+    tensors = [torch.randn(4, 2, generator=g), torch.randn(3, 2, generator=g)]
+    same(ref.collate_fn(list(tensors)), datasets.collate_fn(list(tensors)))
+    # tuples of per-point tensors: the reference's Sequence branch (utils.py:35-40) appends to its samples, so it only serves
+    # append-able non-list sequences; here tuples give the same result it describes: columns + cumulative int32 offset
+    cols = datasets.collate_fn([(torch.ones(4, 3), torch.arange(4)), (torch.zeros(2, 3), torch.arange(2))])
+    assert [tuple(c.shape) for c in cols] == [(6, 3), (6,), (2,)] and cols[2].tolist() == [4, 6] and cols[2].dtype == torch.int32
+    same(ref.collate_fn([[1, 2], [3]]), datasets.collate_fn([[1, 2], [3]]))
+    same(ref.collate_fn(["a", "b"]), datasets.collate_fn(["a", "b"]))
+    # extension, documented: a dict without any offset key gets one from its coord lengths (the reference's datasets add it in Collect)
+    out = datasets.collate_fn([sample(5, False), sample(2, False)])
+    assert out["offset"].tolist() == [5, 7]

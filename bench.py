@@ -205,7 +205,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 ATTAINABLE = {  # structural ceilings of the D = 16 attention kernels as a fraction of the tensor peak
     "attn_fwd": "exp pipe: 64 MMA-flop per ex2 at 16 ex2/clk/SM caps the forward near 0.20 of the bf16 tensor peak",
-    "attn_bwd": "160 MMA-flop per ex2 and 8 B of TMEM reads per score: the backward is capped near 0.5 of the tensor peak",
+    "attn_bwd": "160 MMA-flop per ex2 and 8 B of TMEM reads per score cap the backward near 0.5 of the tensor peak; the measured limiter is "
+                "the issue cadence of its small MMAs (~36 TC-pipe cycles per tcgen05.mma, profiles/r02_ncu_attn_bwd_bq32_ring4_full_metrics.txt)",
 }
 
 

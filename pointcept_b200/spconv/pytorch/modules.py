@@ -1,4 +1,3 @@
-import sys
 from collections import OrderedDict
 
 import torch.nn as nn
@@ -33,8 +32,6 @@ class SparseSequential(SparseModule):
             for idx, module in enumerate(args):
                 self.add_module(str(idx), module)
         for name, module in kwargs.items():
-            if sys.version_info < (3, 6):
-                raise ValueError("kwargs only supported in py36+")
             if name in self._modules:
                 raise ValueError("name exists.")
             self.add_module(name, module)

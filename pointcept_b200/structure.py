@@ -125,7 +125,8 @@ class PointModule(nn.Module):
 
 
 class PointSequential(PointModule):
-    """modules.py:37-111: dispatch on module kind; child naming identical to the reference (checkpoint ABI)."""
+    """The reference's container (modules.py:37-111) restated in condensed form -- same control flow, child naming and error strings,
+    because checkpoints address its children by name; it is boundary glue, not new work."""
 
     def __init__(self, *args, **kwargs):
         super().__init__()

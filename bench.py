@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--no-static-graph", action="store_true", help="DDP without static_graph")
     ap.add_argument("--grad-exchange", default="flat", choices=["flat", "ddp"],
                     help="N > 1: pointcept_b200.reducer.FlatGradReducer (one hook, two collectives per step) or torch DDP")
+    ap.add_argument("--side-priority", type=int, default=-1,
+                    help="CUDA priority of the prefetch stream that prepares the next batch (-1 = high: its host reads are not queued "
+                         "behind the training backlog; 0 = default priority)")
     ap.add_argument("--force-dist", action="store_true",
                     help="N = 1 only: initialise NCCL with world size 1 and run the gradient exchange anyway (measures its overhead)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler (CUPTI) per-kernel breakdown of two extra steps to this file")
@@ -293,7 +296,7 @@ def measure(args, workload, scenes, voxels, steps, warmup, kind="indoor", want_p
     # Coordinate-only preparation (serialization, pooling index plans: the model's only host syncs) of the NEXT batch runs on
     # a side stream while the current batch trains, the way a data loader prefetches: its syncs then wait for the small
     # side-stream queue instead of the whole training backlog.  Work is done every step (nothing is cached across steps).
-    side = torch.cuda.Stream()
+    side = torch.cuda.Stream(priority=args.side_priority)
     main = torch.cuda.current_stream()
 
     def prepare_async(make_inputs):
